@@ -1,0 +1,79 @@
+// Internal helpers shared by the eprecon_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define EP_OK 0
+#define EP_ERR_ARG (-1)
+#define EP_ERR_WORKSPACE (-2)
+#define EP_ERR_CUDA (-3)
+#define EP_ERR_UNSUPPORTED (-4)
+
+#define EP_NUM_SMS 148
+
+#define EP_CHECK_LAUNCH()                                   \
+  do {                                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return EP_ERR_CUDA;             \
+  } while (0)
+
+static inline int ep_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// grid size for a grid-stride kernel: whole waves of resident CTAs, capped by the work
+static inline int ep_grid(long long work_items, int threads, int ctas_per_sm) {
+  long long need = (work_items + threads - 1) / threads;
+  long long cap = (long long)EP_NUM_SMS * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+__device__ __forceinline__ float4 ep_ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ int ep_warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+// Block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32).
+// Returns the exclusive prefix; *total receives the block sum (valid for all threads).
+__device__ __forceinline__ int ep_block_excl_scan(int v, int* smem_warp /*>=33 ints*/, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  int incl = ep_warp_incl_scan(v, lane);
+  if (lane == 31) smem_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nwarp ? smem_warp[lane] : 0;
+    int wi = ep_warp_incl_scan(w, lane);
+    smem_warp[lane] = wi - w;
+    if (lane == 31) smem_warp[32] = wi;
+  }
+  __syncthreads();
+  int out = incl - v + smem_warp[warp];
+  *total = smem_warp[32];
+  __syncthreads();
+  return out;
+}
+
+// torchsparse v2.0.0 coordinate hash (hash_cuda.cu): FNV-1a over (x,y,z,b) as uint32, folded to 60 bits.
+__host__ __device__ __forceinline__ uint64_t ep_sphash(int x, int y, int z, int b) {
+  uint64_t h = 14695981039346656037ULL;
+  h ^= (uint32_t)x; h *= 1099511628211ULL;
+  h ^= (uint32_t)y; h *= 1099511628211ULL;
+  h ^= (uint32_t)z; h *= 1099511628211ULL;
+  h ^= (uint32_t)b; h *= 1099511628211ULL;
+  return (h >> 60) ^ (h & 0x0FFFFFFFFFFFFFFFULL);
+}
+
+// 64-bit mix for open-addressing slots (splitmix64 finaliser)
+__host__ __device__ __forceinline__ uint64_t ep_mix64(uint64_t k) {
+  k ^= k >> 30; k *= 0xbf58476d1ce4e5b9ULL;
+  k ^= k >> 27; k *= 0x94d049bb133111ebULL;
+  k ^= k >> 31;
+  return k;
+}
+
+#define EP_HASH_EMPTY 0xFFFFFFFFFFFFFFFFULL

@@ -1,0 +1,196 @@
+"""Synthetic fragments and weights for parity tests and bench.py.
+
+There is no dataset or checkpoint in the sandbox, so inputs mirror the formulas of the reference's
+data pipeline (datasets/transforms.py:48-77 projection matrices and world_to_aligned_camera,
+:236-260 fragment origin from the frustum hull, :286-297 occupancy = |tsdf| < 0.999) on an analytic
+room scene, and weights are filled deterministically *by parameter name* so that the reference
+modules, the CPU oracle and the CUDA modules can all be loaded with bit-identical values without
+shipping a checkpoint.
+
+Everything here is host-side numpy / torch-CPU; nothing touches the GPU.
+"""
+import math
+import zlib
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+__all__ = ["make_cfg", "make_fragment", "fill_parameters_", "synthetic_state_dict", "PYRAMID_CHANNELS"]
+
+PYRAMID_CHANNELS = (24, 40, 80)  # 1/4, 1/8, 1/16 scale (models/backbone.py:59-77)
+
+
+def make_cfg(n_vox=(96, 96, 96), voxel_size=0.04, num_sample=(15000, 60000, 120000)):
+    """`cfg.MODEL` node with the fields the hot path reads (config/test.yaml:26-45)."""
+    return SimpleNamespace(
+        N_VOX=list(n_vox), VOXEL_SIZE=voxel_size, THRESHOLDS=[0, 0, 0], N_LAYER=3,
+        TRAIN_NUM_SAMPLE=list(num_sample), TEST_NUM_SAMPLE=list(num_sample), POS_WEIGHT=1.5,
+        LW=[1.0, 0.8, 0.64, 0.8],
+        BACKBONE2D=SimpleNamespace(ARC="fpn-mnas-1"),
+        SPARSEREG=SimpleNamespace(DROPOUT=False),
+        FUSION=SimpleNamespace(FUSION_ON=True, HIDDEN_DIM=64, AVERAGE=False, FULL=True),
+    )
+
+
+# ------------------------------------------------------------------------------------------ scene
+_WALL_X, _WALL_Y = 2.9, 2.1
+_BOX_C = np.array([1.9, 0.6, 0.35])
+_BOX_H = np.array([0.45, 0.35, 0.35])
+
+
+def _room_sdf(p):
+    """Signed distance (positive in free space) of an analytic room: floor z=0, walls x=2.9 and
+    y=2.1, one box on the floor.  p: [...,3] float64."""
+    d = np.minimum(np.minimum(p[..., 2], _WALL_X - p[..., 0]), _WALL_Y - p[..., 1])
+    q = np.abs(p - _BOX_C) - _BOX_H
+    box = np.linalg.norm(np.maximum(q, 0.0), axis=-1) + np.minimum(q.max(axis=-1), 0.0)
+    return np.minimum(d, box)
+
+
+def _look_at(eye, target):
+    """Camera-to-world 4x4, camera axes x right / y down / z forward (ScanNet convention)."""
+    f = target - eye
+    f = f / np.linalg.norm(f)
+    up = np.array([0.0, 0.0, 1.0])
+    r = np.cross(f, up)
+    r = r / np.linalg.norm(r)
+    d = np.cross(f, r)
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = r, d, f, eye
+    return m
+
+
+def _rotate_to_xyplane(cam_to_world):
+    """Rotation taking the camera-space image of world +z onto camera -y
+    (datasets/transforms.py:48-57, axis-angle -> matrix via Rodrigues instead of transforms3d)."""
+    z_c = (np.linalg.inv(cam_to_world) @ np.array([0.0, 0.0, 1.0, 0.0]))[:3]
+    axis = np.cross(z_c, np.array([0.0, -1.0, 0.0]))
+    n = np.linalg.norm(axis)
+    if n < 1e-12:
+        return np.eye(3)
+    axis = axis / n
+    theta = math.acos(max(-1.0, min(1.0, -z_c[1] / np.linalg.norm(z_c))))
+    k = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + math.sin(theta) * k + (1 - math.cos(theta)) * (k @ k)
+
+
+def make_fragment(seed=1, n_views=9, image_hw=(480, 640), n_vox=(96, 96, 96), voxel_size=0.04, bs=1,
+                  frag_index=0, scene="scene0000_00", feature_scale=1.0, with_features=True):
+    """One synthetic `inputs` dict + two feature pyramids, shaped as NeuConNet.forward expects
+    (SURVEY.md section 8(b) `inputs` keys).  `frag_index` advances the camera arc by `n_views`
+    keyframes so consecutive fragments of one scene overlap (config 3)."""
+    g = torch.Generator().manual_seed(seed * 1000003 + frag_index)
+    H, W = image_hw
+    # ScanNet colour intrinsics (1296x968, fx~fy~1170, c~(646,490)) resized to WxH
+    # (datasets/transforms.py:83-114: pad 968->972 rows, then scale rows of K by W/1296, H/972)
+    K = np.array([[1170.0 * W / 1296.0, 0, 646.0 * W / 1296.0],
+                  [0, 1170.0 * H / 972.0, 492.0 * H / 972.0],
+                  [0, 0, 1.0]])
+    inputs = {"proj_matrices": [], "vol_origin_partial": [], "vol_origin": [], "world_to_aligned_camera": [],
+              "scene": [], "fragment": []}
+    tsdf_list = [[] for _ in range(3)]
+    occ_list = [[] for _ in range(3)]
+    for b in range(bs):
+        poses = []
+        for v in range(n_views):
+            kf = (frag_index + b * 7) * n_views + v
+            yaw = math.radians(-30.0 + 7.5 * kf)  # keyframe rule: <=15 deg / 0.1 m apart
+            eye = np.array([0.35 + 0.07 * kf * math.cos(yaw * 0.3), -0.4 + 0.07 * kf * math.sin(yaw * 0.3) * 0.5,
+                            1.45 + 0.03 * math.sin(0.9 * kf)])
+            tgt = eye + np.array([math.cos(yaw) * 2.0, math.sin(yaw) * 2.0 + 0.8, -0.75])
+            poses.append(_look_at(eye, tgt))
+        # projection matrices K_s [R|t], s = 0,1,2 <-> 1/4, 1/8, 1/16 (transforms.py:65-77, stride 4)
+        proj = np.zeros((n_views, 3, 4, 4))
+        for v, c2w in enumerate(poses):
+            w2c = np.linalg.inv(c2w)
+            for s in range(3):
+                Ks = K / 4.0 / 2 ** s
+                Ks[2, 2] = 1.0
+                m = w2c.copy()
+                m[:3, :4] = Ks @ w2c[:3, :4]
+                proj[v, s] = m
+        # fragment origin from the frustum hull at max_depth 3 m (transforms.py:236-260)
+        lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+        md = 3.0
+        for c2w in poses:
+            pts = np.array([[0, 0, 0], [(0 - K[0, 2]) * md / K[0, 0], (0 - K[1, 2]) * md / K[1, 1], md],
+                            [(0 - K[0, 2]) * md / K[0, 0], (H - K[1, 2]) * md / K[1, 1], md],
+                            [(W - K[0, 2]) * md / K[0, 0], (0 - K[1, 2]) * md / K[1, 1], md],
+                            [(W - K[0, 2]) * md / K[0, 0], (H - K[1, 2]) * md / K[1, 1], md]])
+            pw = pts @ c2w[:3, :3].T + c2w[:3, 3]
+            lo, hi = np.minimum(lo, pw.min(0)), np.maximum(hi, pw.max(0))
+        center = np.array([(lo[0] + hi[0]) / 2, (lo[1] + hi[1]) / 2, -0.2]) / voxel_size
+        center[:2] = np.round(center[:2] / 8) * 8
+        center[2] = np.floor(center[2] / 8) * 8
+        origin = center.copy()
+        origin[:2] = center[:2] - np.array(n_vox[:2]) // 2
+        vol_origin_partial = origin * voxel_size
+        mid = poses[n_views // 2]
+        w2ac = np.eye(4)
+        w2ac[:3, :3] = _rotate_to_xyplane(mid)
+        w2ac = w2ac @ np.linalg.inv(mid)
+
+        inputs["proj_matrices"].append(torch.from_numpy(proj).float())
+        inputs["vol_origin_partial"].append(torch.from_numpy(vol_origin_partial).float())
+        inputs["vol_origin"].append(torch.zeros(3))
+        inputs["world_to_aligned_camera"].append(torch.from_numpy(w2ac).float())
+        inputs["scene"].append(scene)
+        inputs["fragment"].append(f"{scene}_{frag_index + b}")
+        for l in range(3):
+            dims = [n // 2 ** l for n in n_vox]
+            vs = voxel_size * 2 ** l
+            ii = np.stack(np.meshgrid(*[np.arange(d) for d in dims], indexing="ij"), -1).astype(np.float64)
+            sdf = _room_sdf(ii * vs + vol_origin_partial)
+            tsdf = np.clip(sdf / (3 * vs), -1.0, 1.0).astype(np.float32)
+            tsdf_list[l].append(torch.from_numpy(tsdf))
+            occ_list[l].append(torch.from_numpy(np.abs(tsdf) < 0.999))
+    for k in ("proj_matrices", "vol_origin_partial", "vol_origin", "world_to_aligned_camera"):
+        inputs[k] = torch.stack(inputs[k])
+    inputs["tsdf_list"] = [torch.stack(t) for t in tsdf_list]
+    inputs["occ_list"] = [torch.stack(t) for t in occ_list]
+
+    feats_a = feats_b = None
+    if with_features:
+        def pyramid():
+            out = []
+            for _ in range(n_views):
+                out.append([torch.randn(bs, c, H // 4 // 2 ** s, W // 4 // 2 ** s, generator=g) * feature_scale
+                            for s, c in enumerate(PYRAMID_CHANNELS)])
+            return out
+        feats_a, feats_b = pyramid(), pyramid()
+    return inputs, feats_a, feats_b
+
+
+# ---------------------------------------------------------------------------------------- weights
+def _fill_one(name, p, seed):
+    g = torch.Generator().manual_seed((seed * 2654435761 + zlib.crc32(name.encode())) % (2 ** 63 - 1))
+    shape = tuple(p.shape)
+    if p.ndim == 1:
+        if name.endswith("weight"):
+            v = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            v = 0.05 * torch.randn(shape, generator=g)
+    else:
+        if name.endswith("kernel"):          # torchsparse conv [K,Cin,Cout] / [Cin,Cout]
+            fan_in = int(np.prod(shape[:-1]))
+        elif p.ndim == 2:                    # nn.Linear [out,in]
+            fan_in = shape[1]
+        else:                                # conv2d [Cout,Cin,k,k], spconv [Cout,k,k,k,Cin]
+            fan_in = int(np.prod(shape[1:]))
+        a = math.sqrt(6.0 / fan_in)
+        v = (torch.rand(shape, generator=g) * 2 - 1) * a
+    return v.to(p.dtype)
+
+
+def fill_parameters_(module, seed=1):
+    """Overwrite every parameter of `module` with values that depend only on (name, shape, seed)."""
+    with torch.no_grad():
+        for name, p in sorted(module.named_parameters(), key=lambda kv: kv[0]):
+            p.copy_(_fill_one(name, p, seed))
+    return module
+
+
+def synthetic_state_dict(module, seed=1):
+    fill_parameters_(module, seed)
+    return {k: v.detach().clone() for k, v in module.state_dict().items()}
