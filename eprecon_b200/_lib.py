@@ -1,26 +1,41 @@
-"""ctypes binding of libeprecon_b200.so — the C-ABI boundary (include/eprecon_b200.h).
+"""ctypes binding of libeprecon_b200.so — the C-ABI boundary.
 
-No fallback: if the shared library is missing or a call returns a non-zero status the caller gets
-an exception.  Signatures carry only raw pointers / sizes / a cudaStream_t.
+include/eprecon_b200.h is the single source of truth: the prototypes are parsed from it, so every declared
+symbol must be exported by the library (checked on load) and argument types cannot drift.
+No fallback: if the shared library is missing or a call returns non-zero the caller gets an exception.
 """
 import ctypes
 import os
+import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeprecon_b200.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "eprecon_b200.h")
 
-_P, _I, _I64, _F, _SZ = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+_SCALARS = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float,
+            "size_t": ctypes.c_size_t, "uint64_t": ctypes.c_uint64, "uint32_t": ctypes.c_uint32,
+            "cudaStream_t": ctypes.c_void_p}
 
-# name -> (restype, argtypes); mirrors include/eprecon_b200.h one to one
-SIGNATURES = {
-    "ep_version": (_I, []),
-    "ep_backproject_workspace_bytes": (_SZ, [_I64]),
-    "ep_backproject_count": (_I, [_P, _I64, _P, _F, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
-    "ep_backproject_compact": (_I, [_P, _P, _I64, _I, _P, _P, _P, _P, _P]),
-    "ep_backproject_gather": (_I, [_P, _P, _I64, _P, _I, _I, _I, _I, _I, _P, _F, _P, _I, _P, _I, _P, _P]),
-    "ep_backproject_grid": (_I, [_P, _P, _I64, _I, _I, _I, _I, _P, _F, _P, _P, _P, _P]),
-    "ep_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _P]),
-}
+
+def parse_header(path=HEADER_PATH):
+    """-> {name: (restype, [argtypes])} for every `int|size_t ep_*(...)` prototype in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(int|size_t)\s+(ep_\w+)\s*\(([^)]*)\)\s*;", src):
+        res, name, args = m.group(1), m.group(2), m.group(3).strip()
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    ty = a.replace("const", "").split()[0]
+                    argtypes.append(_SCALARS[ty])
+        out[name] = (_SCALARS[res], argtypes)
+    return out
+
 
 _lib = None
 
@@ -37,7 +52,7 @@ def lib():
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback for the eprecon_b200 hot path)")
         h = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in parse_header().items():
             fn = getattr(h, name)  # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
         _lib = h

@@ -1,0 +1,227 @@
+"""GRUFusion — drop-in for models/gru_fusion.py:8-394 (feature fusion + direct-substitute TSDF fusion).
+
+Same constructor, forward() signature, return structure and per-scene state as the reference.  What changes
+is the mechanism: the reference densifies the current fragment and the cropped global state into two
+[d,d,d,C] fp32 volumes per level (9.7 / 38.9 / 169.9 MB each) just to take their union and re-gather; here the
+union is a compaction over two int32 row-index volumes [d^3] (csrc/union_gather.cu) followed by two row
+gathers, and the ConvGRUs of a level share one set of voxelisations / kernel maps.
+
+Ground-truth bookkeeping (target_tsdf_volume; only used for the reference's loss and its "GT occupancy overlaps
+prediction" guard, models/neucon_network.py:486-490) stays a small dense 1-channel volume in plain torch.
+`panoptic_fusion` / instance-semantic volumes are outside this round's scope.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib, ops, sparse
+from .modules import ConvGRU
+from .ops import stream_ptr
+
+_L = _lib.lib
+
+
+class GRUFusion(nn.Module):
+    def __init__(self, cfg, ch_in=None, direct_substitute=False, trianing=True, ch_voxel=None):
+        super().__init__()
+        self.cfg = cfg
+        self.direct_substitude = direct_substitute
+        self.trianing = trianing
+        if direct_substitute:
+            self.ch_in, self.feat_init = [1, 1, 1], 1
+        else:
+            self.ch_in, self.feat_init = ch_in, 0
+        if ch_voxel is not None:
+            self.ch_voxel = ch_voxel
+            self.ch_img = [x - y for x, y in zip(ch_in, ch_voxel)]
+        self.n_scales = len(cfg.THRESHOLDS) - 1
+        self.scene_name = [None, None, None]
+        self.global_origin = [None, None, None]
+        self.global_volume = [None, None, None]      # dict(C int32 [Ng,3] global voxel ids, F fp32 [Ng,C])
+        self.target_tsdf_volume = [None, None, None]
+        self.return_int32 = False
+        if direct_substitute:
+            self.fusion_nets_voxel = self.fusion_nets_img = None
+        else:
+            self.fusion_nets_voxel = nn.ModuleList()
+            self.fusion_nets_img = nn.ModuleList()
+            for i, ch in enumerate(self.ch_voxel):
+                self.fusion_nets_voxel.append(ConvGRU(hidden_dim=ch, input_dim=ch, pres=1,
+                                                      vres=self.cfg.VOXEL_SIZE * 2 ** (self.n_scales - i)))
+            for i, ch in enumerate(self.ch_img):
+                self.fusion_nets_img.append(ConvGRU(hidden_dim=ch, input_dim=ch, pres=1,
+                                                    vres=self.cfg.VOXEL_SIZE * 2 ** (self.n_scales - i)))
+
+    def reset(self, i, device="cuda"):
+        c = self.ch_in[i]
+        self.global_volume[i] = {"C": torch.zeros((0, 3), dtype=torch.int32, device=device),
+                                 "F": torch.zeros((0, ops.ceil4(c)), dtype=torch.float32, device=device)}
+        self.target_tsdf_volume[i] = {"C": torch.zeros((0, 3), dtype=torch.int64, device=device),
+                                      "F": torch.zeros((0, 1), dtype=torch.float32, device=device)}
+
+    # ------------------------------------------------------------------------------------------------
+    def _union(self, coords_b4, values, c, rel, dims, scale, batch, interval):
+        """Sparse union of the current rows and the in-volume global rows.  Returns level-unit coords (b,x,y,z)
+        int32 [U,4], row ids into current / global (-1 = absent) and the global `valid` mask."""
+        dev = values.device
+        L = _L()
+        st = stream_ptr()
+        dx, dy, dz = dims
+        nvol = dx * dy * dz
+        g = self.global_volume[scale]
+        mode = 1 if self.direct_substitude else 0
+        vol_a = torch.empty(nvol, dtype=torch.int32, device=dev)
+        vol_b = torch.empty(nvol, dtype=torch.int32, device=dev)
+        _lib.check(L.ep_fill_i32(vol_a.data_ptr(), nvol, -1, st), "ep_fill_i32")
+        _lib.check(L.ep_fill_i32(vol_b.data_ptr(), nvol, -1, st), "ep_fill_i32")
+        n = coords_b4.shape[0]
+        _lib.check(L.ep_scatter_rows_to_volume(coords_b4.data_ptr(), 4, 1, n, interval, 0, 0, 0, dx, dy, dz,
+                                               values.data_ptr(), values.stride(0), c, mode, vol_a.data_ptr(), 0, st),
+                   "ep_scatter_rows_to_volume")
+        ng = g["C"].shape[0]
+        valid = torch.zeros(ng, dtype=torch.bool, device=dev)
+        if ng > 0:
+            _lib.check(L.ep_scatter_rows_to_volume(g["C"].data_ptr(), 3, 0, ng, 1, rel[0], rel[1], rel[2], dx, dy, dz,
+                                                   g["F"].data_ptr(), g["F"].stride(0), c, mode, vol_b.data_ptr(),
+                                                   valid.data_ptr(), st), "ep_scatter_rows_to_volume")
+        flags = torch.empty(nvol, dtype=torch.uint8, device=dev)
+        _lib.check(L.ep_union_flags(vol_a.data_ptr(), vol_b.data_ptr(), nvol, flags.data_ptr(), st), "ep_union_flags")
+        sites, u = ops.compact_flags(flags)
+        out_coords = torch.empty((u, 4), dtype=torch.int32, device=dev)
+        row_a = torch.empty(u, dtype=torch.int32, device=dev)
+        row_b = torch.empty(u, dtype=torch.int32, device=dev)
+        if u > 0:
+            _lib.check(L.ep_union_sites(sites.data_ptr(), u, dy, dz, batch, 1, vol_a.data_ptr(), vol_b.data_ptr(),
+                                        out_coords.data_ptr(), row_a.data_ptr(), row_b.data_ptr(), st), "ep_union_sites")
+        return out_coords, row_a, row_b, valid
+
+    def _fuse_targets(self, inputs, i, scale, rel, dims, updated_xyz):
+        """Reference GT fusion (gru_fusion.py:98-112,205-215,324-327) on a dense 1-channel volume."""
+        lvl = self.cfg.N_LAYER - scale - 1
+        occ_t = inputs["occ_list"][lvl][i]
+        tsdf_t = inputs["tsdf_list"][lvl][i][occ_t]
+        coords_t = torch.nonzero(occ_t)
+        tgt = self.target_tsdf_volume[scale]
+        dev = occ_t.device
+        dim = torch.tensor(dims, device=dev)
+        relt = torch.tensor(rel, device=dev)
+        gc = tgt["C"] - relt
+        valid_t = ((gc < dim) & (gc >= 0)).all(dim=-1)
+        cc = torch.cat([gc[valid_t], coords_t])[:, :3]
+        tv = torch.cat([tgt["F"][valid_t], tsdf_t.unsqueeze(-1)])
+        vol = torch.full((dims[0], dims[1], dims[2], 1), 1.0, dtype=tv.dtype, device=dev)
+        if cc.shape[0] > 0:
+            vol[cc[:, 0], cc[:, 1], cc[:, 2]] = tv
+        u = updated_xyz.long()
+        tsdf_target = vol[u[:, 0], u[:, 1], u[:, 2]]
+        occ_target = tsdf_target.abs() < 1
+        # update the GT map
+        v = vol.squeeze(-1)
+        keep = v.abs() < 1
+        tgt["F"] = torch.cat([tgt["F"][valid_t == False], v[keep].unsqueeze(-1)])  # noqa: E712
+        tgt["C"] = torch.cat([tgt["C"][valid_t == False], torch.nonzero(keep) + relt])  # noqa: E712
+        return tsdf_target, occ_target
+
+    def save_mesh(self, scale, outputs, scene):
+        """Scene TSDF as a dense bounding-box volume (gru_fusion.py:217-257), TSDF channel only."""
+        if outputs is None:
+            outputs = dict()
+        if "scene_name" not in outputs:
+            outputs["origin"], outputs["scene_tsdf"], outputs["scene_name"] = [], [], []
+        if scene in outputs["scene_name"]:
+            idx = outputs["scene_name"].index(scene)
+            for k in ("origin", "scene_tsdf", "scene_name"):
+                del outputs[k][idx]
+        outputs["scene_name"].append(scene)
+        g = self.global_volume[scale]
+        c = g["C"].long()
+        max_c, min_c = c.max(0)[0], c.min(0)[0]
+        outputs["origin"].append(min_c * self.cfg.VOXEL_SIZE * (2 ** (self.cfg.N_LAYER - scale - 1)))
+        ind = c - min_c
+        dim = (max_c - min_c + 1).tolist()
+        vol = torch.full(dim, 1.0, dtype=torch.float32, device=c.device)
+        vol[ind[:, 0], ind[:, 1], ind[:, 2]] = g["F"][:, 0]
+        outputs["scene_tsdf"].append(vol)
+        return outputs
+
+    @torch.no_grad()
+    def forward(self, coords, values_in, inputs, scale=2, outputs=None, save_mesh=False, panoptic_infos=None):
+        batch_size = len(inputs["fragment"])
+        interval = 2 ** (self.cfg.N_LAYER - scale - 1)
+        c_all = self.ch_in[scale]
+        dev = values_in.device
+        coords32 = coords.to(torch.int32).contiguous()
+        values_in = values_in if (values_in.stride(1) == 1 and values_in.stride(0) % 4 == 0) else values_in.contiguous()
+        if values_in.stride(0) % 4 != 0:  # e.g. the [N,1] TSDF column
+            tmp = torch.zeros((values_in.shape[0], ops.ceil4(c_all)), dtype=torch.float32, device=dev)
+            tmp[:, :c_all] = values_in
+            values_in = tmp
+        coords_all, values_all, tsdf_all, occ_all = [], [], [], []
+        dims = [int(n) // 2 ** (self.cfg.N_LAYER - scale - 1) for n in self.cfg.N_VOX]
+        for i in range(batch_size):
+            scene = inputs["scene"][i]
+            global_origin = inputs["vol_origin"][i]
+            origin = inputs["vol_origin_partial"][i]
+            if scene != self.scene_name[scale] and self.scene_name[scale] is not None and self.direct_substitude:
+                outputs = self.save_mesh(scale, outputs, self.scene_name[scale])
+            if self.scene_name[scale] is None or scene != self.scene_name[scale]:
+                self.scene_name[scale] = scene
+                self.reset(scale, dev)
+                self.global_origin[scale] = global_origin
+            voxel_size = self.cfg.VOXEL_SIZE * interval
+            rel = ((origin - self.global_origin[scale]) / voxel_size).long().tolist()   # trunc, as .long() does
+            if batch_size == 1:
+                cb, vb = coords32, values_in
+            else:
+                sel = torch.nonzero(coords32[:, 0] == i).squeeze(1)
+                if sel.numel() == 0:
+                    continue
+                cb, vb = coords32[sel].contiguous(), values_in[sel].contiguous()
+            if cb.shape[0] == 0:
+                continue
+            upd, row_a, row_b, valid = self._union(cb, vb, c_all, rel, dims, scale, i, interval)
+            u = upd.shape[0]
+            g = self.global_volume[scale]
+            values = ops.gather_rows(vb, c_all, index=row_a, fill=float(self.feat_init), m=u)
+            gvalues = ops.gather_rows(g["F"], c_all, index=row_b, fill=float(self.feat_init), m=u) if g["F"].shape[0] \
+                else torch.full((u, ops.ceil4(c_all)), float(self.feat_init), dtype=torch.float32, device=dev)
+            if "occ_list" in inputs:
+                tsdf_target, occ_target = self._fuse_targets(inputs, i, scale, rel, dims, upd[:, 1:])
+            else:
+                tsdf_target = occ_target = None
+            if not self.direct_substitude:
+                cv = self.ch_voxel[scale]
+                org = origin.float().view(1, 3).contiguous()
+                w2ac = inputs["world_to_aligned_camera"][i].float().view(1, 4, 4).contiguous()
+                upd0 = upd.clone()
+                upd0[:, 0] = 0
+                r_coords = ops.aligned_coords(upd0, org, voxel_size, w2ac, zero_batch=True)
+                gru_v, gru_i = self.fusion_nets_voxel[scale], self.fusion_nets_img[scale]
+                pc1 = sparse.PointCloud(r_coords, gru_v.vres)
+                pc2 = sparse.PointCloud(pc1.scaled, gru_v.vres)
+                out_v = gru_v.run(gvalues[:, :cv], values[:, :cv], pc1, pc2)
+                out_i = gru_i.run(gvalues[:, cv:c_all], values[:, cv:c_all], pc1, pc2)
+                values = torch.cat([out_v[:, :cv], out_i[:, :c_all - cv]], dim=-1)
+            # update_map (gru_fusion.py:195-204): drop in-volume global rows, append the fused ones
+            relt = torch.tensor(rel, dtype=torch.int32, device=dev)
+            vpad = values if values.shape[1] == g["F"].shape[1] else torch.nn.functional.pad(
+                values, (0, g["F"].shape[1] - values.shape[1]))
+            g["F"] = torch.cat([g["F"][valid == False], vpad])  # noqa: E712
+            g["C"] = torch.cat([g["C"][valid == False], upd[:, 1:] + relt])  # noqa: E712
+            out_c = upd.clone()
+            out_c[:, 1:] *= interval
+            coords_all.append(out_c)
+            values_all.append(values[:, :c_all])
+            if tsdf_target is not None:
+                tsdf_all.append(tsdf_target)
+                occ_all.append(occ_target)
+            if self.direct_substitude and save_mesh:
+                outputs = self.save_mesh(scale, outputs, self.scene_name[scale])
+        if self.direct_substitude:
+            return outputs
+        if not coords_all:
+            return None, None, None, None
+        cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs)) if True else None
+        coords_out = cat(coords_all)
+        if not self.return_int32:
+            coords_out = coords_out.long()
+        return (coords_out, cat(values_all), cat(tsdf_all) if tsdf_all else None, cat(occ_all) if occ_all else None)

@@ -1,0 +1,518 @@
+"""Drop-in mirrors of the reference's sparse building blocks (models/modules.py) on the sm_100a kernels.
+
+Same class names, constructor arguments, forward() signatures and state-dict layout as the reference
+(torchsparse convs own `kernel` [K,Cin,Cout]; spnn.BatchNorm == BatchNorm1d keys; spconv convs own
+`weight` [Cout,k,k,k,Cin] + `bias`), so reference checkpoints load.  The nn containers only hold
+parameters: each forward() is a short program over eprecon_b200.ops / eprecon_b200.sparse.
+
+Numerics follow the reference at inference: BatchNorm uses the statistics of the current fragment
+(the reference evaluates in train mode, main.py:357); running statistics are not updated.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops, sparse
+from .ops import ceil4
+from .tensor import PointTensor  # noqa: F401  (re-exported for callers that build inputs)
+
+__all__ = ["SPVCNN", "SConv3d", "ConvGRU", "SparseSubMConv3d", "Linear4xTrans", "Spares3dELAN", "SubMconv3dBlock",
+           "SparseConv3d_Residual", "Fusion_Block", "ELAN", "Conv2d_Block", "Conv2d_Residual_Block",
+           "Linear_Residual", "BasicConvolutionBlock", "BasicDeconvolutionBlock", "ResidualBlock"]
+
+
+# ------------------------------------------------------------------------------------- parameter holders
+class SpConv3dParams(nn.Module):
+    """Holds `kernel` exactly like torchsparse.nn.Conv3d (models/modules.py:19)."""
+
+    def __init__(self, inc, outc, kernel_size=3, stride=1, dilation=1, transposed=False):
+        super().__init__()
+        self.inc, self.outc, self.ks, self.stride, self.transposed = inc, outc, kernel_size, stride, transposed
+        kv = kernel_size ** 3
+        shape = (kv, inc, outc) if kv > 1 else (inc, outc)
+        self.kernel = nn.Parameter(torch.zeros(*shape))
+        std = 1.0 / math.sqrt((outc if transposed else inc) * kv)
+        self.kernel.data.uniform_(-std, std)
+        self._prep = None
+
+    def prepared(self):
+        k = self.kernel
+        tag = (k.data_ptr(), k._version, k.device)
+        if self._prep is None or self._prep[0] != tag:
+            w = k.detach().float()
+            if w.dim() == 2:
+                w = w.unsqueeze(0)
+            wp = torch.zeros((w.shape[0], self.inc, ceil4(self.outc)), dtype=torch.float32, device=k.device)
+            wp[:, :, :self.outc] = w
+            self._prep = (tag, wp.contiguous())
+        return self._prep[1]
+
+
+class _PrepLinear:
+    """weight [out,in] -> [1, in, ceil4(out)] cache for nn.Linear run through the gather-GEMM kernel."""
+
+    def __init__(self, lin):
+        self.lin, self._prep = lin, None
+
+    def get(self):
+        w = self.lin.weight
+        tag = (w.data_ptr(), w._version, w.device)
+        if self._prep is None or self._prep[0] != tag:
+            o, i = w.shape
+            wp = torch.zeros((1, i, ceil4(o)), dtype=torch.float32, device=w.device)
+            wp[0, :, :o] = w.detach().float().t()
+            self._prep = (tag, wp.contiguous())
+        return self._prep[1]
+
+
+def linear(x, lin, prep, want_stats=False):
+    o, i = lin.weight.shape
+    b = lin.bias.detach() if lin.bias is not None else None
+    return ops.spconv(x, i, None, prep.get(), o, bias=b, want_stats=want_stats)
+
+
+def _bn_ss(part, m, bn):
+    return ops.bn_scale_shift(part, m, bn.weight.detach(), bn.bias.detach(), bn.eps)
+
+
+# ------------------------------------------------------------------------------------------ torchsparse side
+class BasicConvolutionBlock(nn.Module):
+    def __init__(self, inc, outc, ks=3, stride=1, dilation=1):
+        super().__init__()
+        self.net = nn.Sequential(SpConv3dParams(inc, outc, ks, stride, dilation), nn.BatchNorm1d(outc), nn.ReLU(True))
+
+
+class BasicDeconvolutionBlock(nn.Module):
+    def __init__(self, inc, outc, ks=3, stride=1):
+        super().__init__()
+        self.net = nn.Sequential(SpConv3dParams(inc, outc, ks, stride, transposed=True), nn.BatchNorm1d(outc),
+                                 nn.ReLU(True))
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, inc, outc, ks=3, stride=1, dilation=1):
+        super().__init__()
+        self.net = nn.Sequential(SpConv3dParams(inc, outc, ks, stride, dilation), nn.BatchNorm1d(outc), nn.ReLU(True),
+                                 SpConv3dParams(outc, outc, ks, 1, dilation), nn.BatchNorm1d(outc))
+        self.downsample = nn.Sequential() if (inc == outc and stride == 1) else \
+            nn.Sequential(SpConv3dParams(inc, outc, 1, stride), nn.BatchNorm1d(outc))
+        self.relu = nn.ReLU(True)
+
+
+def _conv_bn_relu(x, nbr, seq):
+    """seq = (conv, bn, relu): conv with fused BN statistics, then one BN-apply+ReLU pass in place."""
+    conv, bn = seq[0], seq[1]
+    y, part = ops.spconv(x, conv.inc, nbr, conv.prepared(), conv.outc, want_stats=True)
+    return ops.affine_act(y, conv.outc, ss_a=_bn_ss(part, y.shape[0], bn), relu=True)
+
+
+def _residual_block(x, nbr, blk):
+    """relu( BN(conv2(relu(BN(conv1 x)))) + [BN(conv1x1 x) | x] )  (models/modules.py:46-73)."""
+    net = blk.net
+    t = _conv_bn_relu(x, nbr, net)
+    c2, bn2 = net[3], net[4]
+    u, part_u = ops.spconv(t, c2.inc, nbr, c2.prepared(), c2.outc, want_stats=True)
+    ss_u = _bn_ss(part_u, u.shape[0], bn2)
+    if len(blk.downsample) == 0:
+        return ops.affine_act(u, c2.outc, ss_a=ss_u, b=x, relu=True)
+    cd, bnd = blk.downsample[0], blk.downsample[1]
+    d, part_d = ops.spconv(x, cd.inc, None, cd.prepared(), cd.outc, want_stats=True)
+    return ops.affine_act(u, c2.outc, ss_a=ss_u, b=d, ss_b=_bn_ss(part_d, d.shape[0], bnd), relu=True)
+
+
+class SPVCNN(nn.Module):
+    """Point-voxel U-Net (models/modules.py:75-175).  forward(z) takes any object with `.F` [N,Cin] and `.C`
+    float [N,4]=(x,y,z,b) (e.g. a torchsparse PointTensor) and returns [N, cs[4]]."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.dropout = kwargs["dropout"]
+        cr = kwargs.get("cr", 1.0)
+        cs = [int(cr * x) for x in [32, 64, 128, 96, 96]]
+        self.cs = cs
+        self.in_channels = kwargs["in_channels"]
+        if "pres" in kwargs and "vres" in kwargs:
+            self.pres, self.vres = kwargs["pres"], kwargs["vres"]
+        self.stem = nn.Sequential(SpConv3dParams(self.in_channels, cs[0], 3, 1), nn.BatchNorm1d(cs[0]), nn.ReLU(True))
+        self.stage1 = nn.Sequential(BasicConvolutionBlock(cs[0], cs[0], ks=2, stride=2),
+                                    ResidualBlock(cs[0], cs[1]), ResidualBlock(cs[1], cs[1]))
+        self.stage2 = nn.Sequential(BasicConvolutionBlock(cs[1], cs[1], ks=2, stride=2),
+                                    ResidualBlock(cs[1], cs[2]), ResidualBlock(cs[2], cs[2]))
+        self.up1 = nn.ModuleList([BasicDeconvolutionBlock(cs[2], cs[3], ks=2, stride=2),
+                                  nn.Sequential(ResidualBlock(cs[3] + cs[1], cs[3]), ResidualBlock(cs[3], cs[3]))])
+        self.up2 = nn.ModuleList([BasicDeconvolutionBlock(cs[3], cs[4], ks=2, stride=2),
+                                  nn.Sequential(ResidualBlock(cs[4] + cs[0], cs[4]), ResidualBlock(cs[4], cs[4]))])
+        self.point_transforms = nn.ModuleList([
+            nn.Sequential(nn.Linear(cs[0], cs[2]), nn.BatchNorm1d(cs[2]), nn.ReLU(True)),
+            nn.Sequential(nn.Linear(cs[2], cs[4]), nn.BatchNorm1d(cs[4]), nn.ReLU(True))])
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm1d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        if self.dropout:
+            raise NotImplementedError("SPARSEREG.DROPOUT=True is not on the shipped configs' path")
+        self._pt = [_PrepLinear(self.point_transforms[0][0]), _PrepLinear(self.point_transforms[1][0])]
+
+    def _point_transform(self, i, x):
+        seq = self.point_transforms[i]
+        y, part = linear(x, seq[0], self._pt[i], want_stats=True)
+        return ops.affine_act(y, seq[0].weight.shape[0], ss_a=_bn_ss(part, y.shape[0], seq[1]), relu=True)
+
+    @torch.no_grad()
+    def forward(self, z):
+        cs = self.cs
+        feat = z.F if z.F.stride(0) % 4 == 0 and z.F.stride(1) == 1 else z.F.contiguous()
+        if feat.stride(0) % 4 != 0 or feat.stride(0) < ceil4(self.in_channels):
+            padded = torch.zeros((feat.shape[0], ceil4(self.in_channels)), dtype=torch.float32, device=feat.device)
+            padded[:, :self.in_channels] = feat
+            feat = padded
+        pc = sparse.PointCloud(z.C.float().contiguous(), self.vres)
+        v0 = pc.vox
+        x0 = pc.voxelize(feat, self.in_channels)                                  # initial_voxelize
+        x0 = _conv_bn_relu(x0, v0.kmap_k3(), self.stem)                           # stem
+        idx1, w1 = pc.taps(v0)
+        z0 = sparse.devoxelize(x0, cs[0], idx1, w1)                               # voxel_to_point(x0, z)
+        x1 = pc.voxelize(z0, cs[0])                                               # point_to_voxel(x0, z0)
+        v1, down01, up10 = v0.downsample()
+        x1 = _conv_bn_relu(x1, down01, self.stage1[0].net)
+        x1 = _residual_block(x1, v1.kmap_k3(), self.stage1[1])
+        x1 = _residual_block(x1, v1.kmap_k3(), self.stage1[2])
+        v2, down12, up21 = v1.downsample()
+        x2 = _conv_bn_relu(x1, down12, self.stage2[0].net)
+        x2 = _residual_block(x2, v2.kmap_k3(), self.stage2[1])
+        x2 = _residual_block(x2, v2.kmap_k3(), self.stage2[2])
+        idx4, w4 = pc.taps(v2)
+        z1 = sparse.devoxelize(x2, cs[2], idx4, w4, add=self._point_transform(0, z0))   # z1.F = devox + MLP(z0.F)
+        y3 = pc.voxelize(z1, cs[2], csr=pc.csr_for(v2))                           # point_to_voxel(x2, z1)
+        # up1: transposed conv to stride 2, concat skip x1, two residual blocks
+        dec = self.up1[0].net
+        cat1 = torch.empty((v1.m, cs[3] + cs[1]), dtype=torch.float32, device=feat.device)
+        y, part = ops.spconv(y3, dec[0].inc, up21, dec[0].prepared(), dec[0].outc, want_stats=True, out=cat1, out_col=0)
+        ops.affine_act(cat1, cs[3], ss_a=_bn_ss(part, v1.m, dec[1]), relu=True)
+        cat1[:, cs[3]:] = x1[:, :cs[1]]
+        y3 = _residual_block(cat1, v1.kmap_k3(), self.up1[1][0])
+        y3 = _residual_block(y3, v1.kmap_k3(), self.up1[1][1])
+        dec = self.up2[0].net
+        cat0 = torch.empty((v0.m, cs[4] + cs[0]), dtype=torch.float32, device=feat.device)
+        y, part = ops.spconv(y3, dec[0].inc, up10, dec[0].prepared(), dec[0].outc, want_stats=True, out=cat0, out_col=0)
+        ops.affine_act(cat0, cs[4], ss_a=_bn_ss(part, v0.m, dec[1]), relu=True)
+        cat0[:, cs[4]:] = x0[:, :cs[0]]
+        y4 = _residual_block(cat0, v0.kmap_k3(), self.up2[1][0])
+        y4 = _residual_block(y4, v0.kmap_k3(), self.up2[1][1])
+        z3 = sparse.devoxelize(y4, cs[4], idx1, w1, add=self._point_transform(1, z1))
+        return z3[:, :cs[4]]
+
+
+class SConv3d(nn.Module):
+    """voxelize -> k3 sparse conv -> trilinear devoxelize + Linear (models/modules.py:178-197)."""
+
+    def __init__(self, inc, outc, pres, vres, ks=3, stride=1, dilation=1):
+        super().__init__()
+        self.net = SpConv3dParams(inc, outc, ks, stride, dilation)
+        self.point_transforms = nn.Sequential(nn.Linear(inc, outc))
+        self.pres, self.vres = pres, vres
+        self._pl = _PrepLinear(self.point_transforms[0])
+
+    def run(self, feat, pc, taps_pc=None):
+        """feat [N, inc]; pc: PointCloud to voxelise on; taps_pc: PointCloud whose cached stride-1 taps are used for
+        the devoxelisation (the reference's stale-cache behaviour in ConvGRU.convr, see ConvGRU)."""
+        inc, outc = self.net.inc, self.net.outc
+        x = pc.voxelize(feat, inc)
+        y, _ = ops.spconv(x, inc, pc.vox.kmap_k3(), self.net.prepared(), outc)
+        src = taps_pc if taps_pc is not None else pc
+        idx, w = src.taps(src.vox)
+        lin, _ = linear(feat, self.point_transforms[0], self._pl)
+        return sparse.devoxelize(y, outc, idx, w, add=lin)
+
+    @torch.no_grad()
+    def forward(self, z):
+        pc = sparse.PointCloud(z.C.float().contiguous(), self.vres)
+        out = self.run(z.F.contiguous(), pc)
+        res = PointTensor(out[:, :self.net.outc], pc.scaled)
+        z.C = pc.scaled  # initial_voxelize rebinds z.C to the scaled coordinates (torchsparse_utils.py:33)
+        return res
+
+
+class ConvGRU(nn.Module):
+    """Sparse ConvGRU (models/modules.py:200-222), including the reference's convr quirk: convz rescales the
+    shared PointTensor's coordinates by 1/vres; convr divides AGAIN (so it voxelises at vres^2, every point
+    its own voxel, rows in ascending-hash order) and then devoxelises with convz's cached indices/weights."""
+
+    def __init__(self, hidden_dim=128, input_dim=192 + 128, pres=1, vres=1):
+        super().__init__()
+        self.convz = SConv3d(hidden_dim + input_dim, hidden_dim, pres, vres, 3)
+        self.convr = SConv3d(hidden_dim + input_dim, hidden_dim, pres, vres, 3)
+        self.convq = SConv3d(hidden_dim + input_dim, hidden_dim, pres, vres, 3)
+        self.hidden_dim, self.vres = hidden_dim, vres
+
+    def run(self, h, x, pc1, pc2):
+        """h, x: [U, C] feature matrices; pc1 = points / vres, pc2 = points / vres^2 (shared across the voxel- and
+        image-feature GRUs of a level, which see the same coordinates)."""
+        c = self.hidden_dim
+        u = h.shape[0]
+        hx = torch.empty((u, 2 * c), dtype=torch.float32, device=h.device)
+        hx[:, :c] = h[:, :c]
+        hx[:, c:] = x[:, :c]
+        z_pre = self.convz.run(hx, pc1)
+        r_pre = self.convr.run(hx, pc2, taps_pc=pc1)
+        L = ops._L()
+        st = ops.stream_ptr()
+        rhx = torch.empty_like(hx)
+        ops._lib.check(L.ep_gru_rh(r_pre.data_ptr(), r_pre.stride(0), h.data_ptr(), h.stride(0), x.data_ptr(),
+                                   x.stride(0), u, c, rhx.data_ptr(), rhx.stride(0), st), "ep_gru_rh")
+        q_pre = self.convq.run(rhx, pc1)
+        out = torch.empty((u, ceil4(c)), dtype=torch.float32, device=h.device)
+        ops._lib.check(L.ep_gru_out(z_pre.data_ptr(), z_pre.stride(0), q_pre.data_ptr(), q_pre.stride(0), h.data_ptr(),
+                                    h.stride(0), u, c, out.data_ptr(), out.stride(0), st), "ep_gru_out")
+        return out
+
+    @torch.no_grad()
+    def forward(self, h, x):
+        pts = h.C.float().contiguous()
+        pc1 = sparse.PointCloud(pts, self.vres)
+        pc2 = sparse.PointCloud(pc1.scaled, self.vres)
+        out = self.run(h.F.contiguous(), x.F.contiguous(), pc1, pc2)
+        h.F = out[:, :self.hidden_dim]
+        return h.F
+
+
+# ------------------------------------------------------------------------------------------------ spconv side
+class SubMSites:
+    """Active-site set of a spconv SparseConvTensor: (b,x,y,z) int32 indices + hash table + cached 27-neighbour
+    table.  The reference rebuilds indice pairs on every call (no indice_key, models/modules.py:242,267); build
+    this once per coordinate set and pass it as `sites=` to reuse."""
+
+    def __init__(self, coords_bxyz, spatial_shape):
+        self.coords = coords_bxyz.to(torch.int32).contiguous()
+        self.shape = tuple(int(s) for s in spatial_shape)
+        self.table = ops.HashTable(ops.coord_keys(self.coords, batch_first=True))
+        self._k3 = None
+
+    def kmap(self, ks):
+        if ks == 1:
+            return None
+        if self._k3 is None:
+            self._k3 = ops.kmap_build(self.coords, True, ops.kernel_offsets("subm3", 1, self.coords.device), self.table,
+                                      self.shape)
+        return self._k3
+
+
+class SubMConv3dParams(nn.Module):
+    """Holds `weight` [Cout,k,k,k,Cin] + `bias` like spconv.SubMConv3d."""
+
+    def __init__(self, inc, outc, ks):
+        super().__init__()
+        self.inc, self.outc, self.ks = inc, outc, ks
+        self.weight = nn.Parameter(torch.zeros(outc, ks, ks, ks, inc))
+        self.bias = nn.Parameter(torch.zeros(outc))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(inc * ks ** 3)
+        nn.init.uniform_(self.bias, -bound, bound)
+        self._prep = None
+
+    def prepared(self):
+        w = self.weight
+        tag = (w.data_ptr(), w._version, w.device)
+        if self._prep is None or self._prep[0] != tag:
+            k = self.ks ** 3
+            wp = torch.zeros((k, self.inc, ceil4(self.outc)), dtype=torch.float32, device=w.device)
+            wp[:, :, :self.outc] = w.detach().float().permute(1, 2, 3, 4, 0).reshape(k, self.inc, self.outc)
+            self._prep = (tag, wp.contiguous())
+        return self._prep[1]
+
+    def run(self, x, sites, want_stats=False):
+        return ops.spconv(x, self.inc, sites.kmap(self.ks), self.prepared(), self.outc, bias=self.bias.detach(),
+                          m_out=sites.coords.shape[0], want_stats=want_stats)
+
+
+class SparseSubMConv3d(nn.Module):
+    def __init__(self, C_in, C_out, Kernel, Stride=1):
+        super().__init__()
+        self.sparsesubmconv3d = SubMConv3dParams(C_in, C_out, Kernel)
+        nn.init.xavier_uniform_(self.sparsesubmconv3d.weight)
+        nn.init.constant_(self.sparsesubmconv3d.bias, 0)
+
+    @torch.no_grad()
+    def forward(self, features, coords, spitial_shape, bs, sites=None):
+        sites = sites or SubMSites(coords, spitial_shape)
+        x = _as_rows(features, self.sparsesubmconv3d.inc)
+        y, _ = self.sparsesubmconv3d.run(x, sites)
+        return y[:, :self.sparsesubmconv3d.outc]
+
+
+def _as_rows(x, c):
+    """Row-major fp32 matrix whose row stride is a multiple of 4 floats and covers ceil4(c)."""
+    x = x.float()
+    if x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.stride(0) >= ceil4(c):
+        return x
+    out = torch.zeros((x.shape[0], ceil4(c)), dtype=torch.float32, device=x.device)
+    out[:, :c] = x[:, :c]
+    return out
+
+
+class SubMconv3dBlock(nn.Module):
+    def __init__(self, C_in, C_out, Kernel, Stride, Padding):
+        super().__init__()
+        self.conv = SubMConv3dParams(C_in, C_out, Kernel)
+        self.ln = nn.LayerNorm(C_out)
+        self.act = nn.ReLU()
+
+    def run(self, x, sites, out=None):
+        y, _ = self.conv.run(x, sites)
+        return ops.layernorm(y, self.conv.outc, self.ln.weight.detach(), self.ln.bias.detach(), relu_after=True,
+                             eps=self.ln.eps, out=out)
+
+
+class Spares3dELAN(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        h = int(dim / 2)
+        self.dim = dim
+        self.conv1 = SubMconv3dBlock(dim, dim, 1, 1, 0)
+        self.conv2 = SubMconv3dBlock(dim, dim, 1, 1, 0)
+        self.conv3 = SubMconv3dBlock(dim, h, 3, 1, 1)
+        self.conv4 = SubMconv3dBlock(h, h, 3, 1, 1)
+        self.conv5 = SubMconv3dBlock(h, h, 3, 1, 1)
+        self.conv6 = SubMconv3dBlock(h, h, 3, 1, 1)
+        self.conv7 = SubMconv3dBlock(dim * 4, dim, 1, 1, 0)
+
+    @torch.no_grad()
+    def forward(self, voxel_features_o, voxel_coords_bxyz, batch_size, spitial_shape, sites=None):
+        sites = sites or SubMSites(voxel_coords_bxyz, spitial_shape)
+        d, h = self.dim, int(self.dim / 2)
+        x = _as_rows(voxel_features_o, d)
+        n = x.shape[0]
+        cat = torch.empty((n, 4 * d), dtype=torch.float32, device=x.device)   # [f1 | f2 | c3 | c4 | c5 | c6]
+        self.conv1.run(x, sites, out=cat[:, 0:d])
+        f2 = self.conv2.run(x, sites, out=cat[:, d:2 * d])
+        f = self.conv3.run(f2, sites, out=cat[:, 2 * d:2 * d + h])
+        f = self.conv4.run(f, sites, out=cat[:, 2 * d + h:2 * d + 2 * h])
+        f = self.conv5.run(f, sites, out=cat[:, 2 * d + 2 * h:2 * d + 3 * h])
+        self.conv6.run(f, sites, out=cat[:, 2 * d + 3 * h:2 * d + 4 * h])
+        return self.conv7.run(cat, sites)[:, :d]
+
+
+class SparseConv3d_Residual(nn.Module):
+    def __init__(self, dim, Kernel):
+        super().__init__()
+        self.SConv3d = SparseSubMConv3d(dim, dim, Kernel)
+        self.activation = nn.ReLU()
+        self.norm = nn.LayerNorm(dim)
+
+    @torch.no_grad()
+    def forward(self, x, coords, spitial_shape, bs, sites=None):
+        sites = sites or SubMSites(coords, spitial_shape)
+        c = self.SConv3d.sparsesubmconv3d
+        xr = _as_rows(x, c.inc)
+        y, _ = c.run(xr, sites)
+        return ops.layernorm(y, c.outc, self.norm.weight.detach(), self.norm.bias.detach(), res=xr, relu_before=True,
+                             eps=self.norm.eps)[:, :c.outc]
+
+
+class Linear4xTrans(nn.Module):
+    def __init__(self, C_in, C_out):
+        super().__init__()
+        self.linear1 = nn.Linear(C_in, C_in * 4)
+        self.norm1 = nn.LayerNorm(C_in * 4)
+        self.relu = nn.ReLU()
+        self.linear2 = nn.Linear(C_in * 4, C_in)
+        self.norm2 = nn.LayerNorm(C_in)
+        self.linear3 = nn.Linear(C_in, C_out)
+        self.use_residual = C_in == C_out
+        for lin in (self.linear1, self.linear2, self.linear3):
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.zeros_(lin.bias)
+        self._p = [_PrepLinear(self.linear1), _PrepLinear(self.linear2), _PrepLinear(self.linear3)]
+        self.C_in, self.C_out = C_in, C_out
+
+    @torch.no_grad()
+    def forward(self, x):
+        c = self.C_in
+        xr = _as_rows(x, c)
+        y, _ = linear(xr, self.linear1, self._p[0])
+        ops.layernorm(y, 4 * c, self.norm1.weight.detach(), self.norm1.bias.detach(), relu_after=True, eps=self.norm1.eps)
+        y, _ = linear(y, self.linear2, self._p[1])
+        ops.layernorm(y, c, self.norm2.weight.detach(), self.norm2.bias.detach(), relu_after=True, eps=self.norm2.eps)
+        o, _ = linear(y, self.linear3, self._p[2])
+        if self.use_residual:
+            ops.affine_act(o, self.C_out, b=y)
+        return o[:, :self.C_out]
+
+
+class Linear_Residual(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.linear = nn.Linear(dim, dim)
+        self.activation = nn.ReLU()
+        self.norm = nn.LayerNorm(dim)
+        self._p = _PrepLinear(self.linear)
+        self.dim = dim
+
+    @torch.no_grad()
+    def forward(self, x):
+        xr = _as_rows(x, self.dim)
+        y, _ = linear(xr, self.linear, self._p)
+        return ops.layernorm(y, self.dim, self.norm.weight.detach(), self.norm.bias.detach(), res=xr, relu_before=True,
+                             eps=self.norm.eps)[:, :self.dim]
+
+
+# --------------------------------------------------------------------- dense 2-D blocks (stay on cuDNN)
+class Conv2d_Block(nn.Module):
+    def __init__(self, C_in, C_out, Kernel):
+        super().__init__()
+        self.conv = nn.Conv2d(C_in, C_out, Kernel, padding="same")
+        self.bn = nn.BatchNorm2d(C_out)
+        self.act = nn.ReLU()
+
+    def forward(self, x):
+        return self.act(self.bn(self.conv(x)))
+
+
+class Conv2d_Residual_Block(nn.Module):
+    def __init__(self, C, Kernel):
+        super().__init__()
+        self.conv = nn.Conv2d(C, C, Kernel, padding="same")
+        self.bn = nn.BatchNorm2d(C)
+        self.relu = nn.ReLU()
+
+    def forward(self, x):
+        return self.bn(self.relu(self.conv(x)) + x)
+
+
+class ELAN(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        h = int(dim / 2)
+        self.conv1 = Conv2d_Block(dim, dim, 1)
+        self.conv2 = Conv2d_Block(dim, dim, 1)
+        self.conv3 = Conv2d_Block(dim, h, 3)
+        self.conv4 = Conv2d_Block(h, h, 3)
+        self.conv5 = Conv2d_Block(h, h, 3)
+        self.conv6 = Conv2d_Block(h, h, 3)
+        self.conv7 = Conv2d_Block(dim * 4, dim, 1)
+
+    def forward(self, x):
+        f1, f2 = self.conv1(x), self.conv2(x)
+        c3 = self.conv3(f2)
+        c4 = self.conv4(c3)
+        c5 = self.conv5(c4)
+        c6 = self.conv6(c5)
+        return self.conv7(torch.cat([f1, f2, c3, c4, c5, c6], dim=1))
+
+
+class Fusion_Block(nn.Module):
+    def __init__(self, C):
+        super().__init__()
+        self.conv1 = nn.Conv2d(C, C, 3, padding="same")
+        self.bn1 = nn.BatchNorm2d(C)
+        self.relu = nn.ReLU()
+        self.conv2 = nn.Conv2d(C, C, 1, padding="same")
+        self.bn2 = nn.BatchNorm2d(C)
+        self.ELAN = ELAN(C)
+
+    def forward(self, x):
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        return self.ELAN(out)

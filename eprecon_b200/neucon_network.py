@@ -1,0 +1,235 @@
+"""NeuConNet — drop-in for models/neucon_network.py:25-624 (forward path; TSDF / occupancy refinement).
+
+Same constructor argument (`cfg.MODEL` node), forward() signature and early-return conventions as the reference;
+`outputs['coords']` (int64 [n,4]) and `outputs['tsdf']` ([n,1]) are set only when all three levels succeed.  The
+coarse-to-fine loop keeps int32 coordinates on the device end to end and replaces, per level,
+  upsample + Back_Project + torch.cat      -> x8 coords kernel + fused gather that writes straight into the concat buffer
+  world->aligned-camera matmul + reorder   -> one kernel
+  SPVCNN / GRUFusion / heads               -> eprecon_b200.modules / gru_fusion (gather-GEMM kernels)
+  occupancy mask + nonzero + index         -> flags + scan compaction + row gathers
+Host syncs per level: survivor count of the back-projection, voxel counts of the voxelisations, union size,
+occupied count (each a 4-byte read the reference also performs).
+
+Not built this round (SURVEY.md section 8 f): the panoptic branch (:516-622) — `outputs['panoptic_info']` is None —
+and the training losses (`loss_dict` holds zeros under the reference's keys).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+try:  # the reference logs through loguru; fall back to logging so the import never fails
+    from loguru import logger
+except Exception:  # pragma: no cover
+    import logging
+    logger = logging.getLogger("eprecon_b200")
+
+from . import _lib, ops
+from .gru_fusion import GRUFusion
+from .modules import SPVCNN, Linear4xTrans
+from .occupancy_initialization import Back_Project, Occupancy_Initialization
+from .tensor import PointTensor
+
+_L = _lib.lib
+
+
+class NeuConNet(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.n_scales = len(cfg.THRESHOLDS) - 1
+        alpha = int(self.cfg.BACKBONE2D.ARC.split("-")[-1])
+        ch_in = [80 * alpha, 96 + 40 * alpha + 2, 48 + 24 * alpha + 2, 24 + 24 + 2]
+        channels = [96, 48, 24]
+        ch_initialization = [80, 40, 24]
+        ch_initialization_down = 32
+        n_views = 9
+        panoptic_channels = 48
+        GRU_channels = [x + y for x, y in zip(channels, ch_initialization)]
+        self.channels, self.ch_img = channels, ch_initialization
+        self.back_projection = nn.ModuleList()
+        if self.cfg.FUSION.FUSION_ON:
+            self.gru_fusion = GRUFusion(cfg, ch_in=GRU_channels, ch_voxel=channels)
+            self.gru_fusion.return_int32 = True
+        else:
+            raise NotImplementedError("FUSION.FUSION_ON=False is not a shipped configuration (config/test.yaml:36)")
+        if not self.cfg.FUSION.FULL:
+            raise NotImplementedError("FUSION.FULL=False leaves grid_mask undefined in the reference (neucon_network.py:411)")
+        self.sp_convs = nn.ModuleList()
+        self.tsdf_preds = nn.ModuleList()
+        self.occ_preds = nn.ModuleList()
+        self.panoptic_preds = nn.ModuleList()
+        self.initialization = Occupancy_Initialization(ch_initialization, ch_initialization_down, n_views)
+        for i in range(len(cfg.THRESHOLDS)):
+            self.back_projection.append(Back_Project(ch_initialization[i], materialize_grid=False))
+            self.sp_convs.append(SPVCNN(num_classes=1, in_channels=ch_in[i], pres=1, cr=1 / 2 ** i,
+                                        vres=self.cfg.VOXEL_SIZE * 2 ** (self.n_scales - i),
+                                        dropout=self.cfg.SPARSEREG.DROPOUT))
+            self.tsdf_preds.append(Linear4xTrans(channels[i], 1))
+            self.occ_preds.append(Linear4xTrans(channels[i], 1))
+            self.panoptic_preds.append(Linear4xTrans(GRU_channels[i], panoptic_channels))
+        self._grid_cache = {}
+        self.last_sizes = {}
+
+    # ------------------------------------------------------------------------------------ reference helpers
+    def upsample(self, pre_feat, pre_coords, interval, num=8):
+        """API-compatible x8 upsampling (neucon_network.py:193-214); forward() uses the fused path instead."""
+        with torch.no_grad():
+            c32 = pre_coords.to(torch.int32).contiguous()
+            up_coords = ops.upsample8(c32, interval).to(pre_coords.dtype)
+            n, c = pre_feat.shape
+            idx = torch.arange(n * 8, dtype=torch.int32, device=pre_feat.device)
+            src = pre_feat if pre_feat.stride(1) == 1 else pre_feat.contiguous()
+            up_feat = ops.gather_rows(src, c, index=idx, shift=3)[:, :c]
+        return up_feat, up_coords
+
+    def _init_grid(self, bs, interval, device):
+        key = (tuple(self.cfg.N_VOX), bs, interval, str(device))
+        if key not in self._grid_cache:
+            axes = [torch.arange(0, n, interval, device=device, dtype=torch.int32) for n in self.cfg.N_VOX]
+            g = torch.stack(torch.meshgrid(*axes, indexing="ij"), -1).view(-1, 3)
+            per = [torch.cat([torch.full((g.shape[0], 1), b, dtype=torch.int32, device=device), g], 1) for b in range(bs)]
+            self._grid_cache[key] = (torch.cat(per, 0).contiguous(), tuple(len(a) for a in axes))
+        return self._grid_cache[key]
+
+    def _zero_loss(self, ref):
+        return torch.zeros((), dtype=torch.float32, device=ref.device)
+
+    # ---------------------------------------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward(self, features, features_backbone2d_occ_pano, inputs, outputs, only_train_init=False,
+                only_train_occ=False, init_overlap_count=0):
+        if only_train_init or only_train_occ:
+            raise NotImplementedError("training-only modes are outside the B200 inference path")
+        cfg = self.cfg
+        bs = features[0][0].shape[0]
+        dev = features[0][0].device
+        loss_dict = {}
+        L = _L()
+        st = ops.stream_ptr()
+        origin = inputs["vol_origin_partial"].float().contiguous()
+        w2ac = inputs["world_to_aligned_camera"].float().contiguous()
+
+        # ---------------------------------------------------------------- occupancy initialisation (:240-340)
+        init_stage, min_view_number, occ_init_thresd = 1, 2, 0.3
+        interval = 2 ** (self.n_scales - init_stage)
+        scale = self.n_scales - init_stage
+        up_coords, shape_init = self._init_grid(bs, interval, dev)
+        KRcam = inputs["proj_matrices"][:, :, scale].permute(1, 0, 2, 3).contiguous()
+        init_output = self.initialization(up_coords, origin, cfg.VOXEL_SIZE, features, KRcam, shape_init, init_stage,
+                                          min_view_number)
+        if init_output is None:
+            loss_dict["occupancy_initialization_loss"] = self._zero_loss(origin)
+            logger.warning("no valid points in initialization")
+            outputs["init_overlap_count"] = init_overlap_count
+            return outputs, loss_dict
+        occ_init, coord_init, count_init = init_output
+        src = self.initialization.last["src"]
+        n_fine = up_coords.shape[0]
+        fine = torch.zeros(n_fine, dtype=torch.uint8, device=dev)
+        _lib.check(L.ep_scatter_selected(occ_init.data_ptr(), occ_init.stride(0), src.data_ptr(), occ_init.shape[0],
+                                         occ_init_thresd, fine.data_ptr(), st), "ep_scatter_selected")
+        coarse_dim = shape_init[0] // 2 ** init_stage
+        assert shape_init[0] == shape_init[1] == shape_init[2], "cubic fragment volumes only"
+        sel = torch.empty((bs * coarse_dim ** 3, 4), dtype=torch.int32, device=dev)
+        sel_count = torch.empty(bs + 1, dtype=torch.int32, device=dev)
+        _lib.check(L.ep_init_prune(fine.data_ptr(), bs, coarse_dim, interval * 2 ** init_stage, sel.data_ptr(),
+                                   sel_count.data_ptr(), st), "ep_init_prune")
+        n0 = int(sel_count[bs].item())
+        coord_init_selected = sel[:n0]
+        self.last_sizes = {"init_valid": int(occ_init.shape[0]), "n0": n0}
+
+        # --------------------------------------------------------------------- coarse-to-fine loop (:348-511)
+        pre_feat = pre_coords = None
+        pre_c = 0
+        for i in range(cfg.N_LAYER):
+            interval = 2 ** (self.n_scales - i)
+            scale = self.n_scales - i
+            if i == 0:
+                up_coords = coord_init_selected.contiguous()
+                min_view_number = 2
+                if up_coords.shape[0] == 0:
+                    loss_dict[f"tsdf_occ_loss_{i}"] = self._zero_loss(origin)
+                    logger.warning("no valid points in back_projection: scale {}".format(i))
+                    return outputs, loss_dict
+            else:
+                up_coords = ops.upsample8(pre_coords, interval)
+                min_view_number = 0
+            feats = torch.stack([feat[scale] for feat in features_backbone2d_occ_pano])
+            KRcam = inputs["proj_matrices"][:, :, scale].permute(1, 0, 2, 3).contiguous().float()
+            c_img = feats.shape[2]
+            c_cat = c_img + pre_c
+            res = ops.backproject(up_coords, origin, cfg.VOXEL_SIZE, ops.to_nhwc(feats.float()), KRcam, min_view_number,
+                                  mode="mean", want_src=True, alloc_width=ops.ceil4(c_cat))
+            if res is None:
+                loss_dict[f"tsdf_occ_loss_{i}"] = self._zero_loss(origin)
+                logger.warning("no valid points in back_projection: scale {}".format(i))
+                return outputs, loss_dict
+            up_coords = res["coords"]
+            feat = res["buffer"]                                  # [M, ceil4(c_img + pre_c)]; cols [0,c_img) = volume
+            m = feat.shape[0]
+            if ops.ceil4(c_cat) != c_cat:
+                feat[:, c_cat:].zero_()
+            if i != 0:  # concat the parent's features: up_feat[count >= min] == pre_feat[src >> 3]
+                ops.gather_rows(pre_feat, pre_c, index=res["src"], shift=3, out=feat, out_col=c_img)
+            r_coords = ops.aligned_coords(up_coords, origin, cfg.VOXEL_SIZE, w2ac)
+            feat_v = self.sp_convs[i](PointTensor(feat, r_coords))        # [M, channels[i]]
+            cv = self.channels[i]
+            feat_all = torch.empty((m, cv + c_img), dtype=torch.float32, device=dev)
+            feat_all[:, :cv] = feat_v
+            feat_all[:, cv:] = feat[:, :c_img]
+            up_coords, feat_all, tsdf_target, occ_target = self.gru_fusion(up_coords, feat_all, inputs, i)
+            feat_v = feat_all[:, :cv]
+            tsdf = self.tsdf_preds[i](feat_v)
+            occ = self.occ_preds[i](feat_v)
+            loss_dict[f"tsdf_occ_loss_{i}"] = self._zero_loss(origin)
+
+            # ------------------------------------------------ sparsity for the next level (:454-507)
+            flags = ops.threshold_flags(occ, float(cfg.THRESHOLDS[i]), mode=0)
+            u = up_coords.shape[0]
+            exceed_num = 1.5
+            if bs == 1:
+                index, num = ops.compact_flags(flags)
+                nums = [num]
+            else:
+                nums = [int(flags[up_coords[:, 0] == b].sum().item()) for b in range(bs)]
+                index = None
+            for b, num_batch in enumerate(nums):
+                if num_batch < 500:
+                    logger.warning("no valid points: scale {}".format(i))
+                    return outputs, loss_dict
+                if self.training and num_batch > cfg.TRAIN_NUM_SAMPLE[i] * exceed_num:
+                    logger.warning("exceed too many points: scale {} num_batch {}".format(i, num_batch))
+                    return outputs, loss_dict
+                elif self.training and num_batch > cfg.TRAIN_NUM_SAMPLE[i]:
+                    logger.warning("choice too many points: scale {} num_batch {}".format(i, num_batch))
+                    choice = np.random.choice(num_batch, num_batch - cfg.TRAIN_NUM_SAMPLE[i], replace=False)
+                    rows = torch.nonzero((up_coords[:, 0] == b) & flags.bool()).squeeze(1)
+                    flags[rows[torch.from_numpy(choice).to(dev)]] = 0
+                    index = None
+            if index is None:
+                index, num = ops.compact_flags(flags)
+            if occ_target is not None:
+                ot = occ_target.view(-1)
+                for b in range(bs):
+                    hit = ot[index.long()] if bs == 1 else ot[index.long()][up_coords[index.long(), 0] == b]
+                    if int(hit.sum().item()) == 0:
+                        logger.warning("occ_target is 0: scale {} num_batch {}".format(i, 0))
+                        return outputs, loss_dict
+            pre_coords = ops.gather_coords(up_coords, index)
+            pre_c = cv + 2
+            pre_feat = torch.empty((num, ops.ceil4(pre_c)), dtype=torch.float32, device=dev)
+            if ops.ceil4(pre_c) != pre_c:
+                pre_feat[:, pre_c:].zero_()
+            ops.gather_rows(feat_all, cv, index=index, out=pre_feat, out_col=0)
+            tsdf_c = tsdf if tsdf.stride(1) == 1 else tsdf.contiguous()
+            occ_c = occ if occ.stride(1) == 1 else occ.contiguous()
+            pre_tsdf = ops.gather_rows(tsdf_c, 1, index=index)
+            pre_feat[:, cv] = pre_tsdf[:, 0]
+            pre_feat[:, cv + 1] = ops.gather_rows(occ_c, 1, index=index)[:, 0]
+            self.last_sizes[f"level{i}"] = {"candidates": int(res["count"].shape[0]), "projected": m, "fused": u,
+                                            "occupied": num}
+            if i == cfg.N_LAYER - 1:
+                outputs["coords"] = pre_coords.long()
+                outputs["tsdf"] = pre_tsdf[:, :1]
+        outputs["panoptic_info"] = None
+        return outputs, loss_dict

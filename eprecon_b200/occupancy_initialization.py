@@ -1,13 +1,17 @@
 """Back_Project / Occupancy_Initialization — drop-ins for models/occupancy_initialization.py.
 
-Back_Project.forward keeps the reference signature and 5-tuple (occupancy_initialization.py:189-261);
-the whole body is three kernel launches (count, compact, gather) instead of ~25 ATen ops over
-[V,C,N] intermediates.
+Back_Project.forward keeps the reference signature and 5-tuple (occupancy_initialization.py:189-261); the whole
+body is three kernel launches (count, compact, gather) instead of ~25 ATen ops over [V,C,N] intermediates.
+Occupancy_Initialization.forward (:61-182) keeps the dense 2-D fusion on cuDNN, then
+runs projection + variance gather + the 11 submanifold convs on ONE cached site set / neighbour table.
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
+from .modules import (Conv2d_Block, Conv2d_Residual_Block, Fusion_Block, Spares3dELAN, SparseSubMConv3d, SubMSites,
+                      _as_rows)
 
 
 class Back_Project(nn.Module):
@@ -17,13 +21,15 @@ class Back_Project(nn.Module):
     def __init__(self, dim, materialize_grid=True):
         super().__init__()
         self.materialize_grid = materialize_grid
+        self.last = None
 
-    def forward(self, coords, origin, voxel_size, feats, KRcam, min_view_number):
+    @torch.no_grad()
+    def forward(self, coords, origin, voxel_size, feats, KRcam, min_view_number, out=None, out_col=0):
         n_views, bs, c, h, w = feats.shape
         origin = origin.float().contiguous()
         KRcam = KRcam.float().contiguous()
         res = ops.backproject(coords.to(torch.int32).contiguous(), origin, voxel_size, ops.to_nhwc(feats.float()),
-                              KRcam, min_view_number, mode="mean", want_src=True)
+                              KRcam, min_view_number, mode="mean", want_src=True, out=out, out_col=out_col)
         if res is None:
             return None
         self.last = res  # survivors' source rows / visibility masks for fused callers
@@ -31,3 +37,82 @@ class Back_Project(nn.Module):
         if self.materialize_grid:
             im_grid, mask = ops.backproject_grid(res, origin, voxel_size, KRcam, n_views, bs, h, w)
         return [res["feat"], res["coords"].to(coords.dtype), im_grid, mask, res["count"]]
+
+
+class Occupancy_Initialization(nn.Module):
+    def __init__(self, ch_initialization_all, ch_initialization_down, n_views):
+        super().__init__()
+        ch_all = sum(ch_initialization_all[:3])
+        d = ch_initialization_down
+        self.self_fusion_1x = Fusion_Block(ch_initialization_all[0])
+        self.self_fusion_2x = Fusion_Block(ch_initialization_all[1])
+        self.self_fusion_4x = Fusion_Block(ch_initialization_all[2])
+        self.pool4x = nn.AvgPool2d(2)
+        self.fusion_down = Conv2d_Block(ch_all, d, 1)
+        self.post_fusion_1 = Conv2d_Residual_Block(d, 3)
+        self.post_fusion_2 = Conv2d_Residual_Block(d, 3)
+        self.post_fusion_3 = Conv2d_Residual_Block(d, 3)
+        self.post_fusion_4 = Conv2d_Residual_Block(d, 3)
+        self.similary_1 = Spares3dELAN(d)
+        self.norm0 = nn.BatchNorm1d(d)
+        self.subm1 = SparseSubMConv3d(d, d, 3)
+        self.norm1 = nn.LayerNorm(d)
+        self.subm2 = SparseSubMConv3d(d, d, 3)
+        self.norm2 = nn.LayerNorm(d)
+        self.subm3 = SparseSubMConv3d(d, d, 3)
+        self.norm3 = nn.LayerNorm(d)
+        self.subm4 = SparseSubMConv3d(d, 1, 3)
+        self.norm4 = nn.BatchNorm1d(1)
+        self.relu = nn.ReLU()
+        self.dim = d
+        self.last = None
+
+    def feat_fusion_pre(self, feats_1x, feats_2x, feats_4x):
+        f1 = F.interpolate(self.self_fusion_1x(feats_1x), scale_factor=2, mode="bilinear")
+        f2 = self.self_fusion_2x(feats_2x)
+        f4 = self.pool4x(self.self_fusion_4x(feats_4x))
+        x = self.fusion_down(torch.cat([f1, f2, f4], dim=1))
+        for blk in (self.post_fusion_1, self.post_fusion_2, self.post_fusion_3, self.post_fusion_4):
+            x = blk(x)
+        return x
+
+    @torch.no_grad()
+    def forward(self, coords, origin, voxel_size, features_all, KRcam, shape, stage, min_view_number):
+        feats_1x = torch.stack([f[2] for f in features_all])
+        feats_2x = torch.stack([f[1] for f in features_all])
+        feats_4x = torch.stack([f[0] for f in features_all])
+        n_views, bs = feats_1x.shape[:2]
+        d = self.dim
+        # dense 2-D multi-scale fusion per batch entry (cuDNN; train-mode BN statistics over the views)
+        fused = torch.stack([self.feat_fusion_pre(feats_1x[:, b], feats_2x[:, b], feats_4x[:, b]) for b in range(bs)], 1)
+        origin = origin.float().contiguous()
+        KRcam = KRcam.float().contiguous()
+        res = ops.backproject(coords.to(torch.int32).contiguous(), origin, voxel_size, ops.to_nhwc(fused.float()),
+                              KRcam, min_view_number, mode="meanvar", want_src=True, min_valid=10 * 10 * 10)
+        if res is None:
+            return None
+        self.last = res
+        var = res["feat"]
+        kept = res["coords"]                                           # int32 (b,x,y,z) in 4 cm units
+        subm_coords = kept.clone()
+        subm_coords[:, 1:] = (kept[:, 1:].float() / (2 ** (2 - stage))).to(torch.int32)   # reference: float div, cast
+        occ_chunks = []
+        for b in range(bs):
+            sel = slice(None) if bs == 1 else torch.nonzero(kept[:, 0] == b).squeeze(1)
+            cb = subm_coords[sel].clone()
+            cb[:, 0] = 0
+            sites = SubMSites(cb, shape)
+            m = cb.shape[0]
+            x = _as_rows(var[sel], d)
+            x = ops.affine_act(x.clone(), d, ss_a=ops.bn_scale_shift(ops.colstats(x, d), m, self.norm0.weight.detach(),
+                                                                  self.norm0.bias.detach(), self.norm0.eps))
+            x = _as_rows(self.similary_1(x, cb, 1, shape, sites=sites), d)
+            for conv, norm in ((self.subm1, self.norm1), (self.subm2, self.norm2), (self.subm3, self.norm3)):
+                y, _ = conv.sparsesubmconv3d.run(x, sites)
+                x = ops.layernorm(y, d, norm.weight.detach(), norm.bias.detach(), res=x, relu_before=True, eps=norm.eps)
+            y, part = self.subm4.sparsesubmconv3d.run(x, sites, want_stats=True)
+            y = ops.affine_act(y, 1, ss_a=ops.bn_scale_shift(part, m, self.norm4.weight.detach(),
+                                                             self.norm4.bias.detach(), self.norm4.eps))
+            occ_chunks.append(y[:, :1])
+        occ_init = occ_chunks[0] if bs == 1 else torch.cat(occ_chunks, 0)
+        return [occ_init, kept.to(coords.dtype), res["count"]]

@@ -43,7 +43,7 @@ def to_nhwc(feats):
 
 
 def backproject(coords, origin, voxel_size, feats_nhwc, krcam, min_views, mode="mean", out=None, out_col=0,
-                want_src=False, want_zbar=False, min_valid=1):
+                want_src=False, want_zbar=False, min_valid=1, alloc_width=None):
     """Project + visibility + stable compaction + bilinear gather.
 
     coords int32 [N,4] (b,x,y,z); origin f32 [bs,3]; feats_nhwc f32 [V,bs,H,W,C]; krcam f32 [V,bs,4,4].
@@ -79,7 +79,8 @@ def backproject(coords, origin, voxel_size, feats_nhwc, krcam, min_views, mode="
     _lib.check(L.ep_backproject_compact(coords.data_ptr(), vis.data_ptr(), n, int(min_views), out_coords.data_ptr(),
                                         out_vis.data_ptr(), _ptr(src), ws.data_ptr(), st), "ep_backproject_compact")
     if out is None:
-        out = torch.empty((m, C), dtype=torch.float32, device=dev)
+        # alloc_width: allocate a wider row (the caller concatenates more columns after the C sampled ones)
+        out = torch.empty((m, alloc_width or C), dtype=torch.float32, device=dev)
         out_col = 0
     else:
         _chk(out, torch.float32, "out")
@@ -90,7 +91,7 @@ def backproject(coords, origin, voxel_size, feats_nhwc, krcam, min_views, mode="
                                        {"mean": 0, "meanvar": 1}[mode], out.data_ptr() + 4 * out_col, out.shape[1],
                                        _ptr(zbar), st), "ep_backproject_gather")
     return {"feat": out[:, out_col:out_col + C], "coords": out_coords, "count": count, "vis": out_vis, "src": src,
-            "zbar": zbar, "n_valid": host[:bs]}
+            "zbar": zbar, "n_valid": host[:bs], "buffer": out}
 
 
 def backproject_grid(res, origin, voxel_size, krcam, V, bs, H, W):
@@ -104,3 +105,214 @@ def backproject_grid(res, origin, voxel_size, krcam, V, bs, H, W):
                                               im_grid.data_ptr(), mask.data_ptr(), stream_ptr()),
                "ep_backproject_grid")
     return im_grid, mask
+
+
+# =====================================================================================================
+# generic plumbing
+# =====================================================================================================
+U64_MAX = 0xFFFFFFFFFFFFFFFF
+
+
+def ceil4(c):
+    return (c + 3) // 4 * 4
+
+
+def _L():
+    return _lib.lib()
+
+
+def compact_flags(flags, want_pos=False):
+    """uint8/bool flags [n] -> (index int32 [total] ascending, total) [+ pos int32 [n]]; one host sync."""
+    n = flags.shape[0]
+    dev = flags.device
+    flags = flags.view(torch.uint8) if flags.dtype == torch.bool else flags
+    L = _L()
+    wsb = L.ep_compact_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    index = torch.empty(n, dtype=torch.int32, device=dev)
+    pos = torch.empty(n, dtype=torch.int32, device=dev) if want_pos else None
+    total = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.check(L.ep_compact_flags(flags.data_ptr(), n, index.data_ptr(), _ptr(pos), total.data_ptr(), ws.data_ptr(),
+                                  wsb, stream_ptr()), "ep_compact_flags")
+    t = int(total.item())
+    return (index[:t], t, pos) if want_pos else (index[:t], t)
+
+
+def sort_segments(keys, key_bits, sentinel=U64_MAX, want_seg_of_item=True):
+    """Group items by 64-bit key (int64 storage).  Returns dict(keys_sorted, perm, seg_start, seg_end, seg_of_item, S)."""
+    n = keys.shape[0]
+    dev = keys.device
+    L = _L()
+    wsb = L.ep_sort_segments_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ks = torch.empty(n, dtype=torch.int64, device=dev)
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    seg_start = torch.empty(n, dtype=torch.int32, device=dev)
+    seg_end = torch.empty(n, dtype=torch.int32, device=dev)
+    soi = torch.empty(n, dtype=torch.int32, device=dev) if want_seg_of_item else None
+    nseg = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.check(L.ep_sort_segments(keys.data_ptr(), n, int(key_bits), sentinel, ks.data_ptr(), perm.data_ptr(),
+                                  seg_start.data_ptr(), seg_end.data_ptr(), _ptr(soi), nseg.data_ptr(), ws.data_ptr(),
+                                  wsb, stream_ptr()), "ep_sort_segments")
+    S = int(nseg.item())
+    return {"keys_sorted": ks, "perm": perm, "seg_start": seg_start[:S], "seg_end": seg_end[:S], "seg_of_item": soi,
+            "S": S}
+
+
+class HashTable:
+    """Open-addressing table key(int64 bits) -> row id, load factor <= 0.5."""
+
+    def __init__(self, keys):
+        m = keys.shape[0]
+        cap = 1 << max(4, (2 * m - 1).bit_length())
+        self.cap = cap
+        self.keys = torch.empty(cap, dtype=torch.int64, device=keys.device)
+        self.vals = torch.empty(cap, dtype=torch.int32, device=keys.device)
+        _lib.check(_L().ep_hash_build(keys.data_ptr(), m, self.keys.data_ptr(), self.vals.data_ptr(), cap,
+                                      stream_ptr()), "ep_hash_build")
+
+
+def coord_keys(coords, batch_first):
+    m = coords.shape[0]
+    keys = torch.empty(m, dtype=torch.int64, device=coords.device)
+    _lib.check(_L().ep_coord_keys(coords.data_ptr(), m, int(batch_first), keys.data_ptr(), stream_ptr()),
+               "ep_coord_keys")
+    return keys
+
+
+_OFFSET_CACHE = {}
+
+
+def kernel_offsets(kind, stride, device):
+    """int32 [K,3] offset tables: 'k3' (torchsparse odd volume: z-outer/x-inner), 'k2' (even: x-outer/z-inner),
+    'subm3' (spconv weight order: x-outer/z-inner)."""
+    key = (kind, stride, str(device))
+    if key not in _OFFSET_CACHE:
+        if kind == "k3":
+            o = [[x, y, z] for z in (-1, 0, 1) for y in (-1, 0, 1) for x in (-1, 0, 1)]
+        elif kind == "k2":
+            o = [[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)]
+        elif kind == "subm3":
+            o = [[x, y, z] for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)]
+        else:
+            raise ValueError(kind)
+        _OFFSET_CACHE[key] = (torch.tensor(o, dtype=torch.int32) * stride).to(device)
+    return _OFFSET_CACHE[key]
+
+
+def kmap_build(out_coords, batch_first, offsets, table, shape=None):
+    m, K = out_coords.shape[0], offsets.shape[0]
+    nbr = torch.empty((m, K), dtype=torch.int32, device=out_coords.device)
+    sx, sy, sz = shape if shape is not None else (0, 0, 0)
+    _lib.check(_L().ep_kmap_build(out_coords.data_ptr(), m, int(batch_first), offsets.data_ptr(), K,
+                                  table.keys.data_ptr(), table.vals.data_ptr(), table.cap, int(sx), int(sy), int(sz),
+                                  nbr.data_ptr(), stream_ptr()), "ep_kmap_build")
+    return nbr
+
+
+# =====================================================================================================
+# dense-per-row math
+# =====================================================================================================
+def spconv(x, cin, nbr, W, cout, bias=None, m_out=None, want_stats=False, out=None, out_col=0):
+    """out[j,:cout] = bias + sum_k W[k]^T x[nbr[j,k], :cin].  x [*, ld]; W [K, cin, ceil4(cout)] prepared by the
+    module.  Returns (out [m_out, ceil4(cout)] or view into `out`, bn_partial or None)."""
+    L = _L()
+    K = W.shape[0]
+    if m_out is None:
+        m_out = nbr.shape[0] if nbr is not None else x.shape[0]
+    dev = x.device
+    if out is None:
+        out = torch.empty((m_out, ceil4(cout)), dtype=torch.float32, device=dev)
+        if ceil4(cout) != cout:
+            out[:, cout:].zero_()
+        out_col = 0
+    part = None
+    if want_stats:
+        part = torch.empty((L.ep_spconv_num_row_tiles(m_out), 2, cout), dtype=torch.float32, device=dev)
+    _lib.check(L.ep_spconv_fwd(x.data_ptr(), x.stride(0), cin, _ptr(nbr), K, W.data_ptr(), W.shape[2], cout,
+                               _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
+                               stream_ptr()), "ep_spconv_fwd")
+    return out, part
+
+
+def colstats(x, c):
+    m = x.shape[0]
+    L = _L()
+    part = torch.empty((L.ep_spconv_num_row_tiles(m), 2, c), dtype=torch.float32, device=x.device)
+    _lib.check(L.ep_colstats(x.data_ptr(), x.stride(0), m, c, part.data_ptr(), stream_ptr()), "ep_colstats")
+    return part
+
+
+def bn_scale_shift(part, m, gamma, beta, eps=1e-5):
+    c = part.shape[2]
+    ss = torch.empty((2, c), dtype=torch.float32, device=part.device)
+    _lib.check(_L().ep_bn_finalize(part.data_ptr(), part.shape[0], c, m, float(eps), _ptr(gamma), _ptr(beta),
+                                   ss.data_ptr(), 0, stream_ptr()), "ep_bn_finalize")
+    return ss
+
+
+def affine_act(a, c, ss_a=None, b=None, ss_b=None, relu=False, out=None, out_col=0):
+    m = a.shape[0]
+    if out is None:
+        out, out_col = a, 0
+    _lib.check(_L().ep_affine_act(a.data_ptr(), a.stride(0), _ptr(ss_a), _ptr(b), b.stride(0) if b is not None else 0,
+                                  _ptr(ss_b), int(relu), m, c, out.data_ptr() + 4 * out_col, out.stride(0),
+                                  stream_ptr()), "ep_affine_act")
+    return out
+
+
+def layernorm(x, c, gamma, beta, res=None, relu_before=False, relu_after=False, eps=1e-5, out=None):
+    m = x.shape[0]
+    if out is None:
+        out = x
+    _lib.check(_L().ep_layernorm(x.data_ptr(), x.stride(0), _ptr(res), res.stride(0) if res is not None else 0,
+                                 int(relu_before), _ptr(gamma), _ptr(beta), float(eps), int(relu_after), m, c,
+                                 out.data_ptr(), out.stride(0), stream_ptr()), "ep_layernorm")
+    return out
+
+
+def gather_rows(src, c, index=None, shift=0, fill=0.0, m=None, out=None, out_col=0, src_col=0):
+    if m is None:
+        m = index.shape[0] if index is not None else src.shape[0]
+    if out is None:
+        out = torch.empty((m, ceil4(c)), dtype=torch.float32, device=src.device)
+        if ceil4(c) != c:
+            out[:, c:].zero_()
+        out_col = 0
+    if m > 0:
+        _lib.check(_L().ep_gather_rows(src.data_ptr() + 4 * src_col, src.stride(0), _ptr(index), int(shift),
+                                       float(fill), m, c, out.data_ptr() + 4 * out_col, out.stride(0), stream_ptr()),
+                   "ep_gather_rows")
+    return out
+
+
+def gather_coords(src, index):
+    m = index.shape[0]
+    out = torch.empty((m, 4), dtype=torch.int32, device=src.device)
+    if m > 0:
+        _lib.check(_L().ep_gather_coords(src.data_ptr(), index.data_ptr(), m, out.data_ptr(), stream_ptr()),
+                   "ep_gather_coords")
+    return out
+
+
+def aligned_coords(coords, origin, voxel_size, w2ac, zero_batch=False):
+    n = coords.shape[0]
+    out = torch.empty((n, 4), dtype=torch.float32, device=coords.device)
+    _lib.check(_L().ep_aligned_coords(coords.data_ptr(), n, origin.data_ptr(), float(voxel_size), w2ac.data_ptr(),
+                                      int(zero_batch), out.data_ptr(), stream_ptr()), "ep_aligned_coords")
+    return out
+
+
+def upsample8(coords, interval):
+    n = coords.shape[0]
+    out = torch.empty((n * 8, 4), dtype=torch.int32, device=coords.device)
+    _lib.check(_L().ep_upsample8(coords.data_ptr(), n, int(interval), out.data_ptr(), stream_ptr()), "ep_upsample8")
+    return out
+
+
+def threshold_flags(x, thr, mode=0):
+    n = x.shape[0]
+    flags = torch.empty(n, dtype=torch.uint8, device=x.device)
+    _lib.check(_L().ep_threshold_flags(x.data_ptr(), x.stride(0), n, float(thr), int(mode), flags.data_ptr(),
+                                       stream_ptr()), "ep_threshold_flags")
+    return flags

@@ -1,0 +1,145 @@
+/* eprecon_b200 — C ABI of the B200 (sm_100a) feature-volume hot path of zhen6618/EPRecon.
+ *
+ * The reference has no FFI layer: its boundary is Python nn.Module.forward().  The
+ * drop-in modules in eprecon_b200/*.py keep those signatures and call the entry points below through ctypes
+ * with tensor.data_ptr() and the current cudaStream_t.  Every function
+ *   - takes only raw device pointers, sizes and a stream (no torch types),
+ *   - returns 0 or a negative status (EP_ERR_*), never throws, never allocates (callers pass workspaces sized
+ *     by the matching *_workspace_bytes query), never synchronises,
+ *   - is deterministic (no floating-point atomics).
+ * Each block names the reference code it replaces (file:line under the reference tree).
+ */
+#ifndef EPRECON_B200_H_
+#define EPRECON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_API_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define EP_OK 0
+#define EP_ERR_ARG (-1)
+#define EP_ERR_WORKSPACE (-2)
+#define EP_ERR_CUDA (-3)
+#define EP_ERR_UNSUPPORTED (-4)
+
+int ep_version(void);
+
+/* ---- multi-view back-projection ---------------------------------------------------------------------------
+ * replaces models/occupancy_initialization.py:189-261 (Back_Project.forward), :79-128 (init-stage projection +
+ * masked variance) and ops/back_project.py:5-80 (legacy back_project).
+ * coords int32 [n,4]=(b,x,y,z); origin f32 [bs,3]; krcam f32 [V,bs,4,4]; feats channels-last f32 [V,bs,H,W,C]. */
+size_t ep_backproject_workspace_bytes(int64_t n);
+int ep_backproject_count(const int32_t* coords, int64_t n, const float* origin, float voxel_size,
+                         const float* krcam, int n_views, int bs, int feat_h, int feat_w, int min_views,
+                         float* count, uint32_t* vismask, int32_t* valid_per_batch, int32_t* n_valid_total,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int ep_backproject_compact(const int32_t* coords, const uint32_t* vismask, int64_t n, int min_views,
+                           int32_t* out_coords, uint32_t* out_vis, int32_t* out_src, const void* workspace,
+                           cudaStream_t stream);
+/* mode 0: masked mean over views; mode 1: masked two-pass population variance.  zbar (optional): mean depth. */
+int ep_backproject_gather(const int32_t* out_coords, const uint32_t* out_vis, int64_t m, const float* feats_nhwc,
+                          int channels, int n_views, int bs, int feat_h, int feat_w, const float* origin,
+                          float voxel_size, const float* krcam, int mode, float* out, int ld_out, float* zbar,
+                          cudaStream_t stream);
+int ep_backproject_grid(const int32_t* out_coords, const uint32_t* out_vis, int64_t m, int n_views, int bs,
+                        int feat_h, int feat_w, const float* origin, float voxel_size, const float* krcam,
+                        float* im_grid, uint8_t* mask, cudaStream_t stream);
+int ep_nchw_to_nhwc(const float* in, float* out, int n_img, int channels, int hw, cudaStream_t stream);
+
+/* ---- scan / compaction / sort plumbing ----------------------------------------------------------------------
+ * replaces torch.nonzero / boolean indexing / torch.unique (models/neucon_network.py:304,312,492-501;
+ * ops/torchsparse_utils.py:20; utils.py:172,179). */
+size_t ep_compact_workspace_bytes(int64_t n);
+int ep_compact_flags(const uint8_t* flags, int64_t n, int32_t* out_index, int32_t* out_pos, int32_t* total_dev,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t ep_sort_segments_workspace_bytes(int64_t n);
+int ep_sort_segments(const uint64_t* keys, int64_t n, int key_bits, uint64_t sentinel, uint64_t* keys_sorted,
+                     int32_t* perm, int32_t* seg_start, int32_t* seg_end, int32_t* seg_of_item,
+                     int32_t* n_segments_dev, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- coordinate hashing, tables, kernel maps ----------------------------------------------------------------
+ * replaces torchsparse v2.0.0 sphash / sphashquery / spdownsample / kernel-map search / calc_ti_weights
+ * (ops/torchsparse_utils.py:15-105; inside spnn.Conv3d, models/modules.py:19-181) and spconv indice pairs
+ * (models/modules.py:252,444). */
+int ep_hash_build(const uint64_t* keys, int64_t m, uint64_t* table_keys, int32_t* table_vals, int64_t capacity,
+                  cudaStream_t stream);
+int ep_coord_keys(const int32_t* coords, int64_t m, int batch_first, uint64_t* keys, cudaStream_t stream);
+int ep_point_keys(const float* pts, int64_t n, float vres, float* pts_scaled, uint64_t* keys, cudaStream_t stream);
+int ep_segment_coords(const float* pts_scaled, const int32_t* perm, const int32_t* seg_start, int64_t m,
+                      int32_t* vox_coords, cudaStream_t stream);
+int ep_kmap_build(const int32_t* out_coords, int64_t m_out, int batch_first, const int32_t* offsets, int K,
+                  const uint64_t* table_keys, const int32_t* table_vals, int64_t capacity, int sx, int sy, int sz,
+                  int32_t* nbr, cudaStream_t stream);
+int ep_kmap_inverse(const int32_t* nbr, int64_t m_out, int K, int32_t* inv, cudaStream_t stream);
+int ep_down_keys(const int32_t* coords, int64_t m, int step, uint64_t* keys, cudaStream_t stream);
+int ep_down_unpack(const uint64_t* keys_sorted, const int32_t* seg_start, int64_t m, int32_t* coords,
+                   cudaStream_t stream);
+int ep_devox_prepare(const float* pts_scaled, int64_t n, int stride, const uint64_t* table_keys,
+                     const int32_t* table_vals, int64_t capacity, int32_t* idx, float* weights, cudaStream_t stream);
+int ep_point_query(const float* pts_scaled, int64_t n, int stride, const uint64_t* table_keys,
+                   const int32_t* table_vals, int64_t capacity, int32_t* idx, uint64_t* idx_as_key, int m_sentinel,
+                   cudaStream_t stream);
+
+/* ---- point <-> voxel feature transfer -----------------------------------------------------------------------
+ * replaces torchsparse spvoxelize / spdevoxelize (ops/torchsparse_utils.py:27,58,86,98). */
+int ep_segment_mean(const float* feat, int ld_in, int c, const int32_t* perm, const int32_t* seg_start,
+                    const int32_t* seg_end, int64_t m, float* out, int ld_out, cudaStream_t stream);
+int ep_devoxelize(const float* feat, int ld_in, int c, const int32_t* idx, const float* weights, int64_t n,
+                  const float* add, int ld_add, float* out, int ld_out, cudaStream_t stream);
+
+/* ---- sparse convolution / linear / batch-norm statistics ----------------------------------------------------
+ * replaces spnn.Conv3d forward, spconv SubMConv3d, nn.Linear and the statistics pass of train-mode BatchNorm
+ * (models/modules.py:15-73,89-136,178-197,249-311,401-452; main.py:357). */
+int ep_spconv_num_row_tiles(int64_t m_out);
+int ep_spconv_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, int K, const float* W, int ldw, int cout,
+                  const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, cudaStream_t stream);
+int ep_colstats(const float* x, int ld, int64_t m, int c, float* bn_partial, cudaStream_t stream);
+int ep_bn_finalize(const float* bn_partial, int num_row_tiles, int c, int64_t m, float eps, const float* gamma,
+                   const float* beta, float* scale_shift, float* mean_var, cudaStream_t stream);
+
+/* ---- row-wise / element-wise ----------------------------------------------------------------------------------
+ * BatchNorm apply + residual + ReLU, LayerNorm variants, ConvGRU gates (models/modules.py:207-222), concats,
+ * coordinate transforms (models/neucon_network.py:387-398, models/gru_fusion.py:331-337), x8 upsample (:193-214). */
+int ep_affine_act(const float* a, int ld_a, const float* ss_a, const float* b, int ld_b, const float* ss_b, int relu,
+                  int64_t m, int c, float* out, int ld_out, cudaStream_t stream);
+int ep_layernorm(const float* x, int ld_x, const float* res, int ld_res, int relu_before, const float* gamma,
+                 const float* beta, float eps, int relu_after, int64_t m, int c, float* out, int ld_out,
+                 cudaStream_t stream);
+int ep_gru_rh(const float* r_pre, int ld_r, const float* h, int ld_h, const float* x, int ld_x, int64_t m, int c,
+              float* out, int ld_out, cudaStream_t stream);
+int ep_gru_out(const float* z_pre, int ld_z, const float* q_pre, int ld_q, const float* h, int ld_h, int64_t m, int c,
+               float* out, int ld_out, cudaStream_t stream);
+int ep_gather_rows(const float* src, int ld_src, const int32_t* index, int shift, float fill, int64_t m, int c,
+                   float* out, int ld_out, cudaStream_t stream);
+int ep_gather_coords(const int32_t* src, const int32_t* index, int64_t m, int32_t* out, cudaStream_t stream);
+int ep_aligned_coords(const int32_t* coords, int64_t n, const float* origin, float voxel_size, const float* w2ac,
+                      int zero_batch, float* out, cudaStream_t stream);
+int ep_upsample8(const int32_t* coords, int64_t n, int interval, int32_t* out, cudaStream_t stream);
+int ep_threshold_flags(const float* x, int ld, int64_t n, float thr, int mode, uint8_t* flags, cudaStream_t stream);
+
+/* ---- occupancy-initialisation pruning (models/neucon_network.py:264,298-318; erode/dilate :216-228) ---------- */
+int ep_scatter_selected(const float* logit, int ld, const int32_t* src, int64_t n, float thr, uint8_t* fine,
+                        cudaStream_t stream);
+int ep_init_prune(const uint8_t* fine, int bs, int coarse_dim, int out_scale, int32_t* out_coords, int32_t* out_count,
+                  cudaStream_t stream);
+
+/* ---- GRU-fusion sparse union (models/gru_fusion.py:67-96,321-322; utils.py:176-180) -------------------------- */
+int ep_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t stream);
+int ep_scatter_rows_to_volume(const int32_t* coords, int coord_width, int coord_col0, int64_t n, int div, int ox,
+                              int oy, int oz, int dx, int dy, int dz, const float* feat, int ld, int c, int mode,
+                              int32_t* vol, uint8_t* valid, cudaStream_t stream);
+int ep_union_flags(const int32_t* vol_a, const int32_t* vol_b, int64_t n, uint8_t* flags, cudaStream_t stream);
+int ep_union_sites(const int32_t* sites, int64_t u, int dy, int dz, int batch, int scale, const int32_t* vol_a,
+                   const int32_t* vol_b, int32_t* out_coords, int32_t* row_a, int32_t* row_b, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPRECON_B200_H_ */

@@ -110,3 +110,388 @@ def legacy_depth_channel(zbar):
     zn = (z - mu) / s
     zn[z <= 0] = 0
     return zn
+
+
+# =========================================================================== sparse primitives (shims)
+from torchsparse import SparseTensor  # noqa: E402  (oracle/shims)
+from torchsparse.nn import functional as TF  # noqa: E402
+from torchsparse.nn.utils import get_kernel_offsets  # noqa: E402
+import spconv.pytorch as spconv_shim  # noqa: E402
+
+
+def _bn(x, sd, p, eps=1e-5):
+    """BatchNorm1d with the statistics of the current batch (the reference evaluates in train mode, main.py:357)."""
+    return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], True, 0.1, eps)
+
+
+def _ln(x, sd, p, eps=1e-5):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], eps)
+
+
+def _lin(x, sd, p):
+    return F.linear(x, sd[p + ".weight"], sd[p + ".bias"])
+
+
+def voxelize_points(feat, pts, vres):
+    """initial_voxelize (ops/torchsparse_utils.py:15-35): returns (SparseTensor, scaled points, idx_query, counts)."""
+    scaled = torch.cat([(pts[:, :3] * 1) / vres, pts[:, -1].view(-1, 1)], 1)
+    fl = torch.floor(scaled)
+    h = TF.sphash(fl.int())
+    uniq = torch.unique(h)
+    iq = TF.sphashquery(h, uniq)
+    cnt = TF.spcount(iq.int(), len(uniq))
+    vc = torch.round(TF.spvoxelize(fl, iq, cnt)).int()
+    st = SparseTensor(TF.spvoxelize(feat, iq, cnt), vc, 1)
+    st.cmaps.setdefault(st.stride, st.coords)
+    return st, scaled, iq, cnt
+
+
+def trilinear_taps(scaled, st):
+    """voxel_to_point lookup part (ops/torchsparse_utils.py:71-82): (idx [N,8], w [N,8]) for SparseTensor st."""
+    s = st.s[0]
+    off = get_kernel_offsets(2, st.s, 1)
+    base = torch.cat([torch.floor(scaled[:, :3] / s).int() * s, scaled[:, -1].int().view(-1, 1)], 1)
+    idx = TF.sphashquery(TF.sphash(base, off), TF.sphash(st.C))
+    w = TF.calc_ti_weights(scaled, idx, scale=s).transpose(0, 1).contiguous()
+    return idx.transpose(0, 1).contiguous(), w
+
+
+def points_to_voxels(feat, scaled, st):
+    """point_to_voxel (ops/torchsparse_utils.py:40-63)."""
+    s = st.s[0]
+    h = TF.sphash(torch.cat([torch.floor(scaled[:, :3] / s).int() * s, scaled[:, -1].int().view(-1, 1)], 1))
+    iq = TF.sphashquery(h, TF.sphash(st.C))
+    cnt = TF.spcount(iq.int(), st.C.shape[0])
+    return st._like(TF.spvoxelize(feat, iq, cnt))
+
+
+def _sconv(st, sd, p, ks=3, stride=1, transposed=False):
+    return TF.conv3d(st, sd[p + ".kernel"], None, ks, stride, 1, transposed)
+
+
+def _conv_bn_relu(st, sd, p, **kw):
+    y = _sconv(st, sd, p + ".0", **kw)
+    return y._like(F.relu(_bn(y.F, sd, p + ".1")))
+
+
+def _res_block(st, sd, p):
+    """ResidualBlock (models/modules.py:46-73)."""
+    t = _conv_bn_relu(st, sd, p + ".net")
+    u = _bn(_sconv(t, sd, p + ".net.3").F, sd, p + ".net.4")
+    if (p + ".downsample.0.kernel") in sd:
+        d = _bn(st.F.matmul(sd[p + ".downsample.0.kernel"]), sd, p + ".downsample.1")
+    else:
+        d = st.F
+    return st._like(F.relu(u + d))
+
+
+def _cat(a, b):
+    out = a._like(torch.cat([a.F, b.F], 1))
+    return out
+
+
+def spvcnn(sd, p, feat, pts, vres):
+    """SPVCNN.forward (models/modules.py:148-175).  feat [N,Cin], pts float [N,4]=(x,y,z,b) -> [N, cs4]."""
+    x0, scaled, _, _ = voxelize_points(feat, pts, vres)
+    x0 = _conv_bn_relu(x0, sd, p + ".stem")
+    idx1, w1 = trilinear_taps(scaled, x0)
+    z0 = TF.spdevoxelize(x0.F, idx1, w1)
+    x1 = points_to_voxels(z0, scaled, x0)
+    x1 = _conv_bn_relu(x1, sd, p + ".stage1.0.net", ks=2, stride=2)
+    x1 = _res_block(_res_block(x1, sd, p + ".stage1.1"), sd, p + ".stage1.2")
+    x2 = _conv_bn_relu(x1, sd, p + ".stage2.0.net", ks=2, stride=2)
+    x2 = _res_block(_res_block(x2, sd, p + ".stage2.1"), sd, p + ".stage2.2")
+    idx4, w4 = trilinear_taps(scaled, x2)
+    pt0 = F.relu(_bn(_lin(z0, sd, p + ".point_transforms.0.0"), sd, p + ".point_transforms.0.1"))
+    z1 = TF.spdevoxelize(x2.F, idx4, w4) + pt0
+    y3 = points_to_voxels(z1, scaled, x2)
+    y3 = _conv_bn_relu(y3, sd, p + ".up1.0.net", ks=2, stride=2, transposed=True)
+    y3 = _res_block(_res_block(_cat(y3, x1), sd, p + ".up1.1.0"), sd, p + ".up1.1.1")
+    y4 = _conv_bn_relu(y3, sd, p + ".up2.0.net", ks=2, stride=2, transposed=True)
+    y4 = _res_block(_res_block(_cat(y4, x0), sd, p + ".up2.1.0"), sd, p + ".up2.1.1")
+    pt1 = F.relu(_bn(_lin(z1, sd, p + ".point_transforms.1.0"), sd, p + ".point_transforms.1.1"))
+    return TF.spdevoxelize(y4.F, idx1, w1) + pt1
+
+
+def _sconv3d(sd, p, feat, pts, vres, taps=None):
+    """SConv3d.forward (models/modules.py:189-197); `taps` = cached (idx, w) to reuse (the convr quirk)."""
+    st, scaled, _, _ = voxelize_points(feat, pts, vres)
+    y = _sconv(st, sd, p + ".net")
+    if taps is None:
+        taps = trilinear_taps(scaled, y)
+    out = TF.spdevoxelize(y.F, taps[0], taps[1]) + _lin(feat, sd, p + ".point_transforms.0")
+    return out, scaled, taps
+
+
+def convgru(sd, p, h, x, pts, vres):
+    """ConvGRU.forward (models/modules.py:207-222) including the shared-PointTensor side effects: convz rebinds
+    hx.C to pts/vres and caches stride-1 taps; convr therefore voxelises pts/vres^2 and devoxelises with convz's
+    cached taps (ops/torchsparse_utils.py:33,69-70,97-99); convq sees a fresh PointTensor (original pts)."""
+    hx = torch.cat([h, x], 1)
+    z_pre, scaled1, taps1 = _sconv3d(sd, p + ".convz", hx, pts, vres)
+    r_pre, _, _ = _sconv3d(sd, p + ".convr", hx, scaled1, vres, taps=taps1)
+    z, r = torch.sigmoid(z_pre), torch.sigmoid(r_pre)
+    q_pre, _, _ = _sconv3d(sd, p + ".convq", torch.cat([r * h, x], 1), pts, vres)
+    return (1 - z) * h + z * torch.tanh(q_pre)
+
+
+def linear4x(sd, p, x):
+    """Linear4xTrans.forward (models/modules.py:298-311)."""
+    o = F.relu(_ln(_lin(x, sd, p + ".linear1"), sd, p + ".norm1"))
+    o = F.relu(_ln(_lin(o, sd, p + ".linear2"), sd, p + ".norm2"))
+    o2 = _lin(o, sd, p + ".linear3")
+    return o2 + o if sd[p + ".linear3.weight"].shape[0] == sd[p + ".linear3.weight"].shape[1] else o2
+
+
+# ================================================================================= occupancy initialisation
+def _conv2d_block(sd, p, x):
+    y = F.conv2d(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"], padding="same")
+    return F.relu(F.batch_norm(y, None, None, sd[p + ".bn.weight"], sd[p + ".bn.bias"], True, 0.1, 1e-5))
+
+
+def _elan2d(sd, p, x):
+    f1, f2 = _conv2d_block(sd, p + ".conv1", x), _conv2d_block(sd, p + ".conv2", x)
+    c3 = _conv2d_block(sd, p + ".conv3", f2)
+    c4 = _conv2d_block(sd, p + ".conv4", c3)
+    c5 = _conv2d_block(sd, p + ".conv5", c4)
+    c6 = _conv2d_block(sd, p + ".conv6", c5)
+    return _conv2d_block(sd, p + ".conv7", torch.cat([f1, f2, c3, c4, c5, c6], 1))
+
+
+def _fusion_block(sd, p, x):
+    bn2 = lambda y, q: F.batch_norm(y, None, None, sd[q + ".weight"], sd[q + ".bias"], True, 0.1, 1e-5)  # noqa: E731
+    o = F.relu(bn2(F.conv2d(x, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding="same"), p + ".bn1"))
+    o = F.relu(bn2(F.conv2d(o, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding="same"), p + ".bn2"))
+    return _elan2d(sd, p + ".ELAN", o)
+
+
+def _conv2d_res(sd, p, x):
+    y = F.relu(F.conv2d(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"], padding="same")) + x
+    return F.batch_norm(y, None, None, sd[p + ".bn.weight"], sd[p + ".bn.bias"], True, 0.1, 1e-5)
+
+
+def feat_fusion_pre(sd, p, f1x, f2x, f4x):
+    """Occupancy_Initialization.feat_fusion_pre (models/occupancy_initialization.py:41-58)."""
+    a = F.interpolate(_fusion_block(sd, p + ".self_fusion_1x", f1x), scale_factor=2, mode="bilinear")
+    b = _fusion_block(sd, p + ".self_fusion_2x", f2x)
+    c = F.avg_pool2d(_fusion_block(sd, p + ".self_fusion_4x", f4x), 2)
+    x = _conv2d_block(sd, p + ".fusion_down", torch.cat([a, b, c], 1))
+    for k in (1, 2, 3, 4):
+        x = _conv2d_res(sd, f"{p}.post_fusion_{k}", x)
+    return x
+
+
+def _subm(sd, p, x, coords, shape, ks):
+    conv = spconv_shim.SubMConv3d(sd[p + ".weight"].shape[-1], sd[p + ".weight"].shape[0], ks)
+    conv.weight.data, conv.bias.data = sd[p + ".weight"], sd[p + ".bias"]
+    with torch.no_grad():
+        return conv(spconv_shim.SparseConvTensor(x, coords, shape, 1)).features
+
+
+def _subm_block(sd, p, x, coords, shape, ks):
+    return F.relu(_ln(_subm(sd, p + ".conv", x, coords, shape, ks), sd, p + ".ln"))
+
+
+def occupancy_initialization(sd, p, coords, origin, voxel_size, features_all, krcam, shape, stage, min_view_number):
+    """Occupancy_Initialization.forward (models/occupancy_initialization.py:61-182), bs == 1."""
+    f1x = torch.stack([f[2] for f in features_all])[:, 0]
+    f2x = torch.stack([f[1] for f in features_all])[:, 0]
+    f4x = torch.stack([f[0] for f in features_all])[:, 0]
+    fused = feat_fusion_pre(sd, p, f1x, f2x, f4x).unsqueeze(1)
+    bp = backproject(coords, origin, voxel_size, fused, krcam, min_view_number, mode="meanvar", min_valid=1000)
+    if bp is None:
+        return None
+    sc = (bp["coords"] / (2 ** (2 - stage))).to(coords.dtype)
+    sc[:, 0] = 0
+    x = _bn(bp["feat"], sd, p + ".norm0")
+    e = p + ".similary_1"
+    f1, f2 = _subm_block(sd, e + ".conv1", x, sc, shape, 1), _subm_block(sd, e + ".conv2", x, sc, shape, 1)
+    c3 = _subm_block(sd, e + ".conv3", f2, sc, shape, 3)
+    c4 = _subm_block(sd, e + ".conv4", c3, sc, shape, 3)
+    c5 = _subm_block(sd, e + ".conv5", c4, sc, shape, 3)
+    c6 = _subm_block(sd, e + ".conv6", c5, sc, shape, 3)
+    x = _subm_block(sd, e + ".conv7", torch.cat([f1, f2, c3, c4, c5, c6], -1), sc, shape, 1)
+    for k in (1, 2, 3):
+        y = F.relu(_subm(sd, f"{p}.subm{k}.sparsesubmconv3d", x, sc, shape, 3)) + x
+        x = _ln(y, sd, f"{p}.norm{k}")
+    y = _bn(_subm(sd, p + ".subm4.sparsesubmconv3d", x, sc, shape, 3), sd, p + ".norm4")
+    return {"occ": y, "coords": bp["coords"], "count": bp["count"], "src": bp["src"], "var": bp["feat"]}
+
+
+def init_prune(occ_logit, count, shape_init, min_view_number=2, thr=0.3):
+    """models/neucon_network.py:264,298-318 for bs == 1: -> int64 [n0,4] (b, x*4, y*4, z*4)."""
+    sel = occ_logit.sigmoid().squeeze(-1) > thr
+    vol = torch.zeros(shape_init, dtype=torch.bool)
+    vol[count.view(shape_init) >= min_view_number] = sel
+    v = F.max_pool3d(vol.unsqueeze(0).float(), 2).squeeze(0)
+    ones = torch.ones((1, 1, 3, 3, 3))
+    v = (F.conv3d(v.float()[None, None], ones, padding=1) == 27).squeeze()
+    v = (F.conv3d(v.float()[None, None], ones, padding=1) >= 1).squeeze()
+    v = (F.conv3d(v.float()[None, None], ones, padding=1) >= 1).squeeze()
+    idx = torch.nonzero(v)
+    return torch.cat([torch.zeros(len(idx), 1, dtype=idx.dtype), idx * 4], 1)
+
+
+# =========================================================================================== GRU fusion
+def aligned_points(coords, origin, voxel_size, w2ac, zero_batch=False):
+    """world -> aligned-camera points (models/neucon_network.py:387-398; models/gru_fusion.py:331-337), numpy fp32,
+    one rounding per op, dot products left to right (the order the CUDA kernel fixes)."""
+    c = coords.cpu().numpy()
+    b = c[:, 0].astype(np.int64)
+    org = origin.cpu().numpy().astype(f32)
+    R = w2ac.cpu().numpy().astype(f32)[b]
+    vs = f32(voxel_size)
+    w = [c[:, 1 + k].astype(f32) * vs + org[b, k] for k in range(3)]
+    out = np.zeros((c.shape[0], 4), dtype=f32)
+    for j in range(3):
+        out[:, j] = ((R[:, j, 0] * w[0] + R[:, j, 1] * w[1]) + R[:, j, 2] * w[2]) + R[:, j, 3]
+    out[:, 3] = 0 if zero_batch else c[:, 0].astype(f32)
+    return torch.from_numpy(out)
+
+
+class FusionState:
+    """Per-scene recurrent state of GRUFusion (models/gru_fusion.py:31-38,59-65)."""
+
+    def __init__(self):
+        self.scene = [None] * 3
+        self.origin = [None] * 3
+        self.C = [None] * 3
+        self.F = [None] * 3
+        self.tC = [None] * 3
+        self.tF = [None] * 3
+
+
+def _dense(locs, vals, dims, c, default):
+    d = torch.full([dims[0], dims[1], dims[2], c], float(default), dtype=vals.dtype)
+    if locs.shape[0] > 0:
+        d[locs[:, 0], locs[:, 1], locs[:, 2]] = vals
+    return d
+
+
+def gru_fusion(state, sd, cfg, coords, values_in, inputs, scale, ch_voxel, direct_substitute=False):
+    """GRUFusion.forward (models/gru_fusion.py:259-394) for bs == 1, FUSION.FULL, without the panoptic volumes.
+    Returns (coords int64 [U,4], values [U,C], tsdf_target [U,1], occ_target [U,1])."""
+    interval = 2 ** (cfg.N_LAYER - scale - 1)
+    scene = inputs["scene"][0]
+    if state.scene[scale] is None or scene != state.scene[scale]:
+        state.scene[scale] = scene
+        state.origin[scale] = inputs["vol_origin"][0]
+        c = 1 if direct_substitute else values_in.shape[1]
+        state.C[scale], state.F[scale] = torch.zeros(0, 3, dtype=torch.long), torch.zeros(0, c)
+        state.tC[scale], state.tF[scale] = torch.zeros(0, 3, dtype=torch.long), torch.zeros(0, 1)
+    origin = inputs["vol_origin_partial"][0]
+    voxel_size = cfg.VOXEL_SIZE * interval
+    rel = ((origin - state.origin[scale]) / voxel_size).long()
+    coords_b = torch.div(coords[:, 1:].long(), interval, rounding_mode="floor")
+    dims = [int(n) // 2 ** (cfg.N_LAYER - scale - 1) for n in cfg.N_VOX]
+    dim = torch.tensor(dims)
+    c = values_in.shape[1]
+    init = 1 if direct_substitute else 0
+    gC = state.C[scale] - rel
+    valid = ((gC < dim) & (gC >= 0)).all(-1)
+    gvol = _dense(gC[valid], state.F[scale][valid], dims, c, init)
+    cvol = _dense(coords_b, values_in, dims, c, init)
+    if direct_substitute:
+        upd = torch.nonzero((gvol.abs() < 1).any(-1) | (cvol.abs() < 1).any(-1))
+    else:
+        upd = torch.nonzero((gvol != 0).any(-1) | (cvol != 0).any(-1))
+    lvl = cfg.N_LAYER - scale - 1
+    occ_t = inputs["occ_list"][lvl][0]
+    tsdf_t = inputs["tsdf_list"][lvl][0][occ_t]
+    tC = state.tC[scale] - rel
+    valid_t = ((tC < dim) & (tC >= 0)).all(-1)
+    tvol = _dense(torch.cat([tC[valid_t], torch.nonzero(occ_t)])[:, :3],
+                  torch.cat([state.tF[scale][valid_t], tsdf_t.unsqueeze(-1)]), dims, 1, 1)
+    values = cvol[upd[:, 0], upd[:, 1], upd[:, 2]]
+    gvalues = gvol[upd[:, 0], upd[:, 1], upd[:, 2]]
+    tsdf_target = tvol[upd[:, 0], upd[:, 1], upd[:, 2]]
+    occ_target = tsdf_target.abs() < 1
+    if not direct_substitute:
+        cv = ch_voxel[scale]
+        vres = cfg.VOXEL_SIZE * 2 ** (len(cfg.THRESHOLDS) - 1 - scale)
+        upd0 = torch.cat([torch.zeros(len(upd), 1, dtype=upd.dtype), upd], 1)
+        pts = aligned_points(upd0, origin.view(1, 3), voxel_size, inputs["world_to_aligned_camera"][:1], zero_batch=True)
+        vv = convgru(sd, f"gru_fusion.fusion_nets_voxel.{scale}", gvalues[:, :cv], values[:, :cv], pts, vres)
+        vi = convgru(sd, f"gru_fusion.fusion_nets_img.{scale}", gvalues[:, cv:], values[:, cv:], pts, vres)
+        values = torch.cat([vv, vi], -1)
+    state.F[scale] = torch.cat([state.F[scale][valid == False], values])  # noqa: E712
+    state.C[scale] = torch.cat([state.C[scale][valid == False], upd + rel])  # noqa: E712
+    tv = tvol.squeeze(-1)
+    state.tF[scale] = torch.cat([state.tF[scale][valid_t == False], tv[tv.abs() < 1].unsqueeze(-1)])  # noqa: E712
+    state.tC[scale] = torch.cat([state.tC[scale][valid_t == False], torch.nonzero(tv.abs() < 1) + rel])  # noqa: E712
+    out_c = torch.cat([torch.zeros(len(upd), 1, dtype=upd.dtype), upd * interval], 1)
+    return out_c, values, tsdf_target, occ_target
+
+
+# ============================================================================================ NeuConNet
+def upsample8(pre_feat, pre_coords, interval):
+    """NeuConNet.upsample (models/neucon_network.py:193-214)."""
+    pos = [[1], [2], [3], [1, 2], [1, 3], [2, 3], [1, 2, 3]]
+    up_c = pre_coords.unsqueeze(1).repeat(1, 8, 1)
+    for k, cols in enumerate(pos):
+        for col in cols:
+            up_c[:, k + 1, col] += interval
+    up_f = pre_feat.unsqueeze(1).expand(-1, 8, -1).reshape(-1, pre_feat.shape[1])
+    return up_f, up_c.view(-1, 4)
+
+
+def neucon_forward(sd, cfg, features, features_b, inputs, state, trace=None, teacher=None):
+    """NeuConNet.forward, TSDF path, bs == 1 (models/neucon_network.py:230-511).  `trace` (dict) receives every stage's
+    tensors; `teacher` (a previous trace) overrides the data-dependent decisions (init selection, occupancy masks)
+    so two implementations can be compared stage by stage on identical sparsity."""
+    t = trace if trace is not None else {}
+    n_scales = len(cfg.THRESHOLDS) - 1
+    origin = inputs["vol_origin_partial"]
+    axes = [torch.arange(0, n, 2) for n in cfg.N_VOX]
+    g = torch.stack(torch.meshgrid(*axes, indexing="ij")).view(3, -1)
+    shape_init = tuple(len(a) for a in axes)
+    coords = torch.cat([torch.zeros(1, g.shape[1], dtype=torch.long), g]).t().contiguous().int()
+    kr = inputs["proj_matrices"][:, :, 1].permute(1, 0, 2, 3).contiguous()
+    init = occupancy_initialization(sd, "initialization", coords, origin, cfg.VOXEL_SIZE, features, kr, shape_init, 1, 2)
+    if init is None:
+        return None
+    t["init"] = init
+    sel = init_prune(init["occ"], init["count"], shape_init)
+    t["init_selected"] = sel
+    pre_feat = pre_coords = None
+    channels = [96, 48, 24]
+    out = {}
+    for i in range(cfg.N_LAYER):
+        interval, scale = 2 ** (n_scales - i), n_scales - i
+        if i == 0:
+            up_coords, minv = sel.int(), 2
+        else:
+            up_feat, up_coords = upsample8(pre_feat, pre_coords, interval)
+            minv = 0
+        feats = torch.stack([f[scale] for f in features_b])
+        kr = inputs["proj_matrices"][:, :, scale].permute(1, 0, 2, 3).contiguous()
+        bp = backproject(up_coords, origin, cfg.VOXEL_SIZE, feats, kr, minv)
+        if bp is None:
+            return None
+        volume, up_coords = bp["feat"], bp["coords"]
+        feat = torch.cat([volume, up_feat[bp["count"] >= minv]], 1) if i != 0 else volume
+        pts = aligned_points(up_coords, origin, cfg.VOXEL_SIZE, inputs["world_to_aligned_camera"])
+        vres = cfg.VOXEL_SIZE * 2 ** (n_scales - i)
+        fv = spvcnn(sd, f"sp_convs.{i}", feat, pts, vres)
+        feat_all = torch.cat([fv, volume], -1)
+        t[f"l{i}_pre_gru"] = {"coords": up_coords, "feat_in": feat, "pts": pts, "spvcnn": fv}
+        up_coords, feat_all, tsdf_target, occ_target = gru_fusion(state, sd, cfg, up_coords, feat_all, inputs, i, channels)
+        fv = feat_all[:, :channels[i]]
+        tsdf = linear4x(sd, f"tsdf_preds.{i}", fv)
+        occ = linear4x(sd, f"occ_preds.{i}", fv)
+        occupancy = occ.squeeze(1) > cfg.THRESHOLDS[i]
+        if teacher is not None:
+            occupancy = teacher[f"l{i}"]["occupancy"]
+        t[f"l{i}"] = {"coords": up_coords, "feat_all": feat_all, "tsdf": tsdf, "occ": occ, "occupancy": occupancy,
+                      "occ_target": occ_target}
+        num = int(occupancy.sum())
+        if num < 500 or num > cfg.TRAIN_NUM_SAMPLE[i] * 1.5:
+            return None
+        assert num <= cfg.TRAIN_NUM_SAMPLE[i], "keep synthetic occupancy under the caps (np.random drop not restated)"
+        if occ_target[occupancy].sum() == 0:
+            return None
+        pre_coords = up_coords[occupancy]
+        pre_feat = torch.cat([fv[occupancy], tsdf[occupancy], occ[occupancy]], 1)
+        if i == cfg.N_LAYER - 1:
+            out["coords"], out["tsdf"] = pre_coords, tsdf[occupancy]
+    return out
