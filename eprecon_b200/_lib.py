@@ -39,6 +39,24 @@ def parse_header(path=HEADER_PATH):
 
 _lib = None
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim); anything not listed launches one kernel
+KERNELS_PER_CALL = {"ep_version": 0, "ep_backproject_workspace_bytes": 0, "ep_compact_workspace_bytes": 0,
+                    "ep_sort_segments_workspace_bytes": 0, "ep_spconv_num_row_tiles": 0, "ep_backproject_count": 3,
+                    "ep_compact_flags": 3, "ep_sort_segments": 12, "ep_hash_build": 2}
+LAUNCHES = {"n": 0}
+
+
+class _Counted:
+    """ctypes function proxy that counts the kernels each call launches."""
+
+    def __init__(self, fn, k):
+        self._fn, self._k = fn, k
+
+    def __call__(self, *a):
+        LAUNCHES["n"] += self._k
+        return self._fn(*a)
+
+
 
 class EpreconError(RuntimeError):
     pass
@@ -55,6 +73,7 @@ def lib():
         for name, (res, args) in parse_header().items():
             fn = getattr(h, name)  # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
+            setattr(h, name, _Counted(fn, KERNELS_PER_CALL.get(name, 1)))
         _lib = h
     return _lib
 

@@ -69,6 +69,8 @@ class NeuConNet(nn.Module):
             self.panoptic_preds.append(Linear4xTrans(GRU_channels[i], panoptic_channels))
         self._grid_cache = {}
         self.last_sizes = {}
+        self.trace = None      # set to a dict to capture every stage's tensors (parity tests)
+        self.teacher = None    # oracle trace whose data-dependent decisions (init selection, occupancy) are forced
 
     # ------------------------------------------------------------------------------------ reference helpers
     def upsample(self, pre_feat, pre_coords, interval, num=8):
@@ -136,6 +138,12 @@ class NeuConNet(nn.Module):
                                    sel_count.data_ptr(), st), "ep_init_prune")
         n0 = int(sel_count[bs].item())
         coord_init_selected = sel[:n0]
+        tr, th = self.trace, self.teacher
+        if tr is not None:
+            tr["init"] = {"occ": occ_init, "coords": coord_init, "count": count_init, "var": self.initialization.last["feat"]}
+            tr["init_selected"] = coord_init_selected
+        if th is not None:
+            coord_init_selected = th["init_selected"].to(dev).to(torch.int32).contiguous()
         self.last_sizes = {"init_valid": int(occ_init.shape[0]), "n0": n0}
 
         # --------------------------------------------------------------------- coarse-to-fine loop (:348-511)
@@ -174,6 +182,9 @@ class NeuConNet(nn.Module):
             r_coords = ops.aligned_coords(up_coords, origin, cfg.VOXEL_SIZE, w2ac)
             feat_v = self.sp_convs[i](PointTensor(feat, r_coords))        # [M, channels[i]]
             cv = self.channels[i]
+            if tr is not None:
+                tr[f"l{i}_pre_gru"] = {"coords": up_coords, "feat_in": feat[:, :c_cat], "pts": r_coords, "spvcnn": feat_v,
+                                       "count": res["count"]}
             feat_all = torch.empty((m, cv + c_img), dtype=torch.float32, device=dev)
             feat_all[:, :cv] = feat_v
             feat_all[:, cv:] = feat[:, :c_img]
@@ -186,6 +197,11 @@ class NeuConNet(nn.Module):
             # ------------------------------------------------ sparsity for the next level (:454-507)
             flags = ops.threshold_flags(occ, float(cfg.THRESHOLDS[i]), mode=0)
             u = up_coords.shape[0]
+            if tr is not None:
+                tr[f"l{i}"] = {"coords": up_coords, "feat_all": feat_all, "tsdf": tsdf, "occ": occ,
+                               "occupancy": flags.bool().clone(), "occ_target": occ_target}
+            if th is not None:
+                flags = th[f"l{i}"]["occupancy"].to(dev).to(torch.uint8).contiguous()
             exceed_num = 1.5
             if bs == 1:
                 index, num = ops.compact_flags(flags)

@@ -9,6 +9,29 @@ from . import _lib
 
 __all__ = ["stream_ptr", "to_nhwc", "backproject"]
 
+# bench.py instrumentation: when PROFILE is a dict, the two dominant kernel families record a CUDA-event pair per
+# launch on the launching stream ("events") or, in a separate untimed pass, their algorithmic work ("work").
+PROFILE = None
+
+
+def _prof_begin(kind):
+    if PROFILE is None or PROFILE.get("mode") != "events":
+        return None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    PROFILE.setdefault(kind, []).append((e0, e1))
+    return e1
+
+
+def _prof_end(e1):
+    if e1 is not None:
+        e1.record()
+
+
+def _prof_work(kind, fn):
+    if PROFILE is not None and PROFILE.get("mode") == "work":
+        PROFILE.setdefault(kind + "_work", []).append(fn())
+
 
 def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
@@ -86,10 +109,15 @@ def backproject(coords, origin, voxel_size, feats_nhwc, krcam, min_views, mode="
         _chk(out, torch.float32, "out")
         assert out.shape[0] == m and out_col % 4 == 0 and out_col + C <= out.shape[1]
     zbar = torch.empty(m, dtype=torch.float32, device=dev) if want_zbar else None
+    # algorithmic bytes of the whole back-projection call: maps + KRt + coords in + count out + rows out
+    _prof_work("bp_gather", lambda: {"bytes": 4 * V * C * H * W + 64 * V + 20 * n + (16 + 4 * C) * m, "n_in": n,
+                                     "n_out": m, "C": C})
+    _e = _prof_begin("bp_gather")
     _lib.check(L.ep_backproject_gather(out_coords.data_ptr(), out_vis.data_ptr(), m, feats_nhwc.data_ptr(), C, V, bs,
                                        H, W, origin.data_ptr(), float(voxel_size), krcam.data_ptr(),
                                        {"mean": 0, "meanvar": 1}[mode], out.data_ptr() + 4 * out_col, out.shape[1],
                                        _ptr(zbar), st), "ep_backproject_gather")
+    _prof_end(_e)
     return {"feat": out[:, out_col:out_col + C], "coords": out_coords, "count": count, "vis": out_vis, "src": src,
             "zbar": zbar, "n_valid": host[:bs], "buffer": out}
 
@@ -229,9 +257,13 @@ def spconv(x, cin, nbr, W, cout, bias=None, m_out=None, want_stats=False, out=No
     part = None
     if want_stats:
         part = torch.empty((L.ep_spconv_num_row_tiles(m_out), 2, cout), dtype=torch.float32, device=dev)
+    _prof_work("spconv", lambda: {"pairs": int((nbr >= 0).sum().item()) if nbr is not None else int(m_out),
+                                  "cin": cin, "cout": cout, "K": K, "m_out": int(m_out), "m_in": int(x.shape[0])})
+    _e = _prof_begin("spconv")
     _lib.check(L.ep_spconv_fwd(x.data_ptr(), x.stride(0), cin, _ptr(nbr), K, W.data_ptr(), W.shape[2], cout,
                                _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
                                stream_ptr()), "ep_spconv_fwd")
+    _prof_end(_e)
     return out, part
 
 

@@ -435,7 +435,7 @@ def upsample8(pre_feat, pre_coords, interval):
     return up_f, up_c.view(-1, 4)
 
 
-def neucon_forward(sd, cfg, features, features_b, inputs, state, trace=None, teacher=None):
+def neucon_forward(sd, cfg, features, features_b, inputs, state, trace=None, teacher=None, max_level=None):
     """NeuConNet.forward, TSDF path, bs == 1 (models/neucon_network.py:230-511).  `trace` (dict) receives every stage's
     tensors; `teacher` (a previous trace) overrides the data-dependent decisions (init selection, occupancy masks)
     so two implementations can be compared stage by stage on identical sparsity."""
@@ -492,6 +492,8 @@ def neucon_forward(sd, cfg, features, features_b, inputs, state, trace=None, tea
             return None
         pre_coords = up_coords[occupancy]
         pre_feat = torch.cat([fv[occupancy], tsdf[occupancy], occ[occupancy]], 1)
-        if i == cfg.N_LAYER - 1:
+        if i == cfg.N_LAYER - 1 or (max_level is not None and i >= max_level):
             out["coords"], out["tsdf"] = pre_coords, tsdf[occupancy]
+            out["level"] = i
+            break
     return out

@@ -1,0 +1,62 @@
+"""C-ABI contract checks that need no GPU: the library loads and exports every symbol the header declares; the host-side
+mirrors keep the reference's names and state-dict layout; the product path fails loudly without CUDA."""
+import os
+import re
+
+import pytest
+import torch
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from eprecon_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 40
+    L = _lib.lib()
+    for name in protos:
+        assert hasattr(L, name), name
+    assert L.ep_version() >= 100
+    hdr = open(_lib.HEADER_PATH).read()
+    assert len(re.findall(r"\bep_\w+\s*\(", hdr)) == len(protos)      # the parser saw every prototype
+
+
+def test_header_has_no_torch_types():
+    from eprecon_b200 import _lib
+    hdr = re.sub(r"/\*.*?\*/", " ", open(_lib.HEADER_PATH).read(), flags=re.S)   # prototypes only, comments stripped
+    assert "torch" not in hdr.lower() and "at::" not in hdr and "Tensor" not in hdr
+
+
+def test_state_dict_layout_mirrors_reference_names():
+    from eprecon_b200 import synth
+    from eprecon_b200.neucon_network import NeuConNet
+    sd = NeuConNet(synth.make_cfg()).state_dict()
+    assert sd["sp_convs.0.stem.0.kernel"].shape == (27, 80, 32)                    # torchsparse [K,Cin,Cout]
+    assert sd["sp_convs.1.stage1.0.net.0.kernel"].shape == (8, 16, 16)
+    assert sd["sp_convs.2.up1.0.net.0.kernel"].shape == (8, 32, 24)
+    assert sd["initialization.subm1.sparsesubmconv3d.weight"].shape == (32, 3, 3, 3, 32)   # spconv [Cout,k,k,k,Cin]
+    assert sd["initialization.similary_1.conv7.conv.weight"].shape == (32, 1, 1, 1, 128)
+    assert sd["gru_fusion.fusion_nets_voxel.0.convz.net.kernel"].shape == (27, 192, 96)
+    assert sd["gru_fusion.fusion_nets_img.2.convq.point_transforms.0.weight"].shape == (24, 48)
+    assert sd["tsdf_preds.0.linear1.weight"].shape == (384, 96)
+    assert "sp_convs.0.stem.1.running_mean" in sd
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_cuda():
+    from eprecon_b200 import _lib, synth
+    from eprecon_b200.occupancy_initialization import Back_Project
+    inputs, fa, fb = synth.make_fragment(seed=1, image_hw=(120, 160), n_vox=(32, 32, 32))
+    coords = torch.zeros((8, 4), dtype=torch.int32)
+    feats = torch.stack([f[2] for f in fb])
+    kr = inputs["proj_matrices"][:, :, 2].permute(1, 0, 2, 3).contiguous()
+    with pytest.raises(_lib.EpreconError):
+        Back_Project(80)(coords, inputs["vol_origin_partial"], 0.04, feats, kr, 2)
+
+
+def test_oracle_is_not_imported_by_the_product():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "eprecon_b200")
+    for fn in os.listdir(root):
+        if fn.endswith(".py"):
+            src = open(os.path.join(root, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
