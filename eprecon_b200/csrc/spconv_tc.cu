@@ -1,0 +1,311 @@
+// Sparse 3-D convolution on the 5th-gen tensor cores: gather -> tcgen05.mma (kind::tf32, fp32 accumulate in
+// TMEM) -> fused epilogue.  Same contract as ep_spconv_fwd (csrc/spconv.cu):
+//     out[j, :] = bias + sum_k W[k]^T . in[nbr[j, k], :]
+//
+// One CTA owns 128 output rows x NT output channels (NT <= 128, multiple of 16).  For every kernel offset with a
+// neighbour in the tile and every 16-channel slab of Cin, all 256 threads gather the A slab (rows through the
+// neighbour table, 16-byte loads) and copy the matching weight slab into shared memory in the UMMA canonical
+// K-major / no-swizzle layout (8x16B core matrices); one elected thread then issues the MMAs and commits them to an
+// mbarrier, so the gather of slab s+1 overlaps the tensor work of slab s (3-stage ring).  Accumulators never leave
+// TMEM until the epilogue (tcgen05.ld), which adds the bias, stores the rows and emits per-CTA column sums / sums of
+// squares for batch-statistics BatchNorm.
+//
+// Precision: kind::tf32 reads the top 19 bits of each fp32 operand.  PREC == 1 rounds both operands to tf32
+// (rel. error 2^-11 per product); PREC == 3 is the error-compensated split  a = a_hi + a_lo, b = b_hi + b_lo,
+// a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo  (dropped term 2^-22), i.e. fp32-grade results at 3 MMAs per slab --
+// this keeps the 1e-3 end-to-end parity budget of the north star through ~40 stacked layers.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TMR = 128;      // output rows per CTA (UMMA M)
+constexpr int KCT = 16;       // input channels per stage (2 MMAs of K = 8)
+constexpr int NSTAGE = 3;
+constexpr int TC_THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B stored contiguously;
+// LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_round(float x) {  // round-to-nearest-even to 10 mantissa bits
+  uint32_t u = __float_as_uint(x);
+  u += 0x00000FFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(TC_THREADS)
+spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*/, const int* __restrict__ nbr, int K,
+                 const float* __restrict__ w_hi, const float* __restrict__ w_lo, int nq /*ceil(cin/4)*/,
+                 int npad /*total padded cout*/, int nt /*columns of this launch's tile*/, int tmem_cols, int cout,
+                 const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m_out,
+                 float* __restrict__ bn_partial, int bn_rows) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // per stage: A_hi [4][128][4 floats] (8 KB) | A_lo (8 KB, PREC==3) | B_hi [4][nt][4] | B_lo
+  const int a_bytes = (KCT / 4) * TMR * 16;
+  const int b_bytes = (KCT / 4) * nt * 16;
+  const int stage_bytes = (PREC == 3 ? 2 : 1) * (a_bytes + b_bytes);
+  __shared__ uint64_t mma_done[NSTAGE];
+  __shared__ uint64_t all_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_nbr[TMR];
+  __shared__ int s_any;
+  __shared__ float s_red[8][128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * TMR;
+  const int col0 = blockIdx.y * nt;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(&mma_done[s], 1);
+    mbar_init(&all_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(TMR >> 4) << 24);
+
+  const int nchunk = (cin4 + KCT - 1) / KCT;
+  int it = 0;  // pipeline slot counter (uniform across the CTA)
+  for (int k = 0; k < K; ++k) {
+    __syncthreads();
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    if (tid < TMR) {
+      const int j = row0 + tid;
+      int r = -1;
+      if (j < m_out) r = nbr ? nbr[(size_t)j * K + k] : j;
+      s_nbr[tid] = r;
+      if (r >= 0) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) continue;
+    for (int c = 0; c < nchunk; ++c, ++it) {
+      const int stage = it % NSTAGE;
+      if (it >= NSTAGE) mbar_wait(&mma_done[stage], ((it / NSTAGE) - 1) & 1);  // MMAs that read this stage retired
+      uint8_t* sbase = smem_raw + (size_t)stage * stage_bytes;
+      float4* a_hi = reinterpret_cast<float4*>(sbase);
+      float4* a_lo = reinterpret_cast<float4*>(sbase + a_bytes);
+      float4* b_hi = reinterpret_cast<float4*>(sbase + (PREC == 3 ? 2 : 1) * a_bytes);
+      float4* b_lo = reinterpret_cast<float4*>(sbase + (PREC == 3 ? 2 : 1) * a_bytes + b_bytes);
+      // ---- gather A: 4 chunks x 128 rows of 16 B; consecutive threads -> consecutive rows (conflict-free STS)
+#pragma unroll
+      for (int i = 0; i < (KCT / 4) * TMR / TC_THREADS; ++i) {
+        const int e = tid + i * TC_THREADS;
+        const int row = e & (TMR - 1), jq = e >> 7;
+        const int col = c * KCT + jq * 4;
+        const int src = s_nbr[row];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src >= 0 && col < cin4) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)src * ld_in + col));
+        if (PREC == 3) {
+          float4 h = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                                 __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+          a_hi[jq * TMR + row] = h;
+          a_lo[jq * TMR + row] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        } else {
+          a_hi[jq * TMR + row] = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+        }
+      }
+      // ---- weights: [k][q][npad][4] -> B stage [4][nt][4]; contiguous 16-byte copies
+      for (int e = tid; e < (KCT / 4) * nt; e += TC_THREADS) {
+        const int jq = e / nt, n = e - jq * nt;
+        const int q = c * (KCT / 4) + jq;
+        float4 vh = make_float4(0.f, 0.f, 0.f, 0.f), vl = vh;
+        if (q < nq) {
+          const size_t off = (((size_t)k * nq + q) * npad + col0 + n) * 4;
+          vh = __ldg(reinterpret_cast<const float4*>(w_hi + off));
+          if (PREC == 3) vl = __ldg(reinterpret_cast<const float4*>(w_lo + off));
+        }
+        b_hi[e] = vh;
+        if (PREC == 3) b_lo[e] = vl;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy STS -> visible to the tensor core
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+#pragma unroll
+        for (int kk = 0; kk < KCT / 8; ++kk) {
+          const uint32_t a_off = kk * 2 * TMR * 16, b_off = kk * 2 * nt * 16;
+          const uint64_t dah = umma_desc(sa_hi + a_off, TMR * 16, 128), dbh = umma_desc(sb_hi + b_off, nt * 16, 128);
+          umma_tf32(tmem_d, dah, dbh, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          if (PREC == 3) {
+            const uint64_t dal = umma_desc(sa_lo + a_off, TMR * 16, 128), dbl = umma_desc(sb_lo + b_off, nt * 16, 128);
+            umma_tf32(tmem_d, dal, dbh, idesc, 1u);
+            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+          }
+        }
+        umma_commit(&mma_done[stage]);  // arrives when the MMAs issued so far have finished reading smem
+      }
+    }
+  }
+  // ---- all MMAs done?
+  if (tid == 0) umma_commit(&all_done);
+  __syncthreads();
+  if (it > 0) mbar_wait(&all_done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: warp w reads TMEM lanes [32*(w%4), +32) and columns of half (w/4)
+  const int q = warp & 3, half = warp >> 2;
+  const int row = row0 + q * 32 + lane;
+  const int ncol_half = (nt / 16 + 1) / 2 * 16;  // columns handled by half 0 (multiple of 16)
+  const int cbeg = half == 0 ? 0 : ncol_half, cend = half == 0 ? min(ncol_half, nt) : nt;
+  for (int cb = cbeg; cb < cend; cb += 16) {
+    float v[16];
+    if (it > 0) tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+    else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+    float s[16], sq[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = col0 + cb + i;
+      const float val = v[i] + ((bias && col < cout) ? bias[col] : 0.f);
+      const bool ok = row < m_out && col < cout;
+      if (ok) out[(size_t)row * ld_out + col] = val;
+      s[i] = ok ? val : 0.f;
+      sq[i] = ok ? val * val : 0.f;
+    }
+    if (bn_partial) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          s[i] += __shfl_xor_sync(0xffffffffu, s[i], d);
+          sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], d);
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { s_red[q][cb + i] = s[i]; s_red[4 + q][cb + i] = sq[i]; }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (bn_partial && tid < nt) {
+    const int col = col0 + tid;
+    if (col < cout) {
+      const float s = (s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]);
+      const float sq = (s_red[4][tid] + s_red[5][tid]) + (s_red[6][tid] + s_red[7][tid]);
+      // bn_partial is sized for 64-row tiles: this CTA fills entry 2*bx and zeroes 2*bx+1
+      const int r0 = 2 * blockIdx.x;
+      bn_partial[((size_t)r0 * 2 + 0) * cout + col] = s;
+      bn_partial[((size_t)r0 * 2 + 1) * cout + col] = sq;
+      if (r0 + 1 < bn_rows) {
+        bn_partial[((size_t)(r0 + 1) * 2 + 0) * cout + col] = 0.f;
+        bn_partial[((size_t)(r0 + 1) * 2 + 1) * cout + col] = 0.f;
+      }
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols));
+  }
+}
+
+inline int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Weights must be pre-arranged as float[K][nq][npad][4] (w[k][q][n][i] = W[k][4q+i][n], zero padded; npad = cout
+// rounded up to a multiple of 16, and of 128 when larger than 128).  w_lo is only read when prec == 3.
+// bn_partial: NULL or float[ep_spconv_num_row_tiles(m_out), 2, cout].
+int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, int K, const float* w_hi,
+                     const float* w_lo, int npad, int cout, const float* bias, float* out, int ld_out, int64_t m_out,
+                     float* bn_partial, int prec, cudaStream_t stream) {
+  if (m_out <= 0 || cin < 1 || cout < 1 || K < 1 || ld_in % 4 != 0 || npad % 16 != 0 || npad < cout) return EP_ERR_ARG;
+  if (!nbr && K != 1) return EP_ERR_ARG;
+  if (prec != 1 && prec != 3) return EP_ERR_ARG;
+  if (prec == 3 && !w_lo) return EP_ERR_ARG;
+  const int cin4 = (cin + 3) / 4 * 4;
+  if (cin4 > ld_in) return EP_ERR_ARG;
+  int nt = npad;
+  if (npad > 128) {
+    if (npad % 128 != 0) return EP_ERR_ARG;
+    nt = 128;
+  }
+  const int tmem_cols = pow2_cols(nt);
+  const size_t stage = (size_t)(prec == 3 ? 2 : 1) * ((KCT / 4) * TMR * 16 + (KCT / 4) * nt * 16);
+  const size_t smem = stage * NSTAGE;
+  cudaError_t e;
+  if (prec == 3) e = cudaFuncSetAttribute(spconv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  else e = cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return EP_ERR_CUDA;
+  dim3 grid(ep_div_up(m_out, TMR), npad / nt);
+  const int bn_rows = ep_div_up(m_out, 64);
+  if (prec == 3)
+    spconv_tc_kernel<3><<<grid, TC_THREADS, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, (cin + 3) / 4, npad, nt,
+                                                           tmem_cols, cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows);
+  else
+    spconv_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, (cin + 3) / 4, npad, nt,
+                                                           tmem_cols, cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
+}  // extern "C"

@@ -5,6 +5,8 @@ body is three kernel launches (count, compact, gather) instead of ~25 ATen ops o
 Occupancy_Initialization.forward (:61-182) keeps the dense 2-D fusion on cuDNN, then
 runs projection + variance gather + the 11 submanifold convs on ONE cached site set / neighbour table.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -66,6 +68,32 @@ class Occupancy_Initialization(nn.Module):
         self.relu = nn.ReLU()
         self.dim = d
         self.last = None
+        self._graphs = {}
+        self.use_cuda_graph = os.environ.get("EPRECON_NO_GRAPH", "") == ""
+
+    def _fusion_graphed(self, f1, f2, f4):
+        """feat_fusion_pre has static shapes (9 views x fixed pyramids): capture its ~150 cuDNN/ATen launches in one
+        CUDA graph per (shape, weights) and replay it -- the launch-bound part of the init stage becomes 1 launch."""
+        key = (tuple(f1.shape), tuple(f2.shape), tuple(f4.shape), str(f1.device), self.fusion_down.conv.weight.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            s1, s2, s4 = torch.empty_like(f1), torch.empty_like(f2), torch.empty_like(f4)
+            s1.copy_(f1), s2.copy_(f2), s4.copy_(f4)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.feat_fusion_pre(s1, s2, s4)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.feat_fusion_pre(s1, s2, s4)
+            g = self._graphs[key] = (graph, s1, s2, s4, out)
+        graph, s1, s2, s4, out = g
+        s1.copy_(f1), s2.copy_(f2), s4.copy_(f4)
+        graph.replay()
+        return out
 
     def feat_fusion_pre(self, feats_1x, feats_2x, feats_4x):
         f1 = F.interpolate(self.self_fusion_1x(feats_1x), scale_factor=2, mode="bilinear")
@@ -86,8 +114,9 @@ class Occupancy_Initialization(nn.Module):
         # dense 2-D multi-scale fusion per batch entry (cuDNN; train-mode BN statistics over the views)
         # fp32 convolutions (no TF32): the fused map feeds a variance whose 1e-3 parity budget TF32 would use up
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            fused = torch.stack([self.feat_fusion_pre(feats_1x[:, b], feats_2x[:, b], feats_4x[:, b])
-                                 for b in range(bs)], 1)
+            fuse = self._fusion_graphed if (self.use_cuda_graph and feats_1x.is_cuda) else self.feat_fusion_pre
+            fused = torch.stack([fuse(feats_1x[:, b].contiguous(), feats_2x[:, b].contiguous(),
+                                      feats_4x[:, b].contiguous()) for b in range(bs)], 1)
         origin = origin.float().contiguous()
         KRcam = KRcam.float().contiguous()
         res = ops.backproject(coords.to(torch.int32).contiguous(), origin, voxel_size, ops.to_nhwc(fused.float()),

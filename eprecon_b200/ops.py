@@ -3,6 +3,8 @@
 Each wrapper validates dtype / contiguity / device, allocates outputs with torch (plumbing), passes
 raw device pointers + the current CUDA stream, and raises on a non-zero status.  No CPU fallback.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -241,6 +243,37 @@ def kmap_build(out_coords, batch_first, offsets, table, shape=None):
 # =====================================================================================================
 # dense-per-row math
 # =====================================================================================================
+# "ffma" = fp32 CUDA-core gather-GEMM (csrc/spconv.cu); "tf32x3" / "tf32" = tcgen05 tensor-core kernel (csrc/spconv_tc.cu)
+SPCONV_IMPL = os.environ.get("EPRECON_SPCONV", "tf32x3")
+_UMMA_CACHE = {}
+
+
+def _umma_weights(W, cout, prec):
+    """FFMA-layout weights [K, cin, ceil4(cout)] -> (w_hi, w_lo, npad) in the UMMA slab layout [K][ceil(cin/4)][npad][4]."""
+    key = (W.data_ptr(), W._version, tuple(W.shape), prec)
+    hit = _UMMA_CACHE.get(key)
+    if hit is None:
+        K, cin, _ = W.shape
+        npad = (cout + 15) // 16 * 16
+        if npad > 128:
+            npad = (cout + 127) // 128 * 128
+        nq = (cin + 3) // 4
+        wp = torch.zeros((K, nq * 4, npad), dtype=torch.float32, device=W.device)
+        wp[:, :cin, :cout] = W[:, :, :cout]
+        u = wp.view(torch.int32)
+        if prec == 1:
+            hi = ((u + 0xFFF + ((u >> 13) & 1)) & ~0x1FFF).view(torch.float32)
+            lo = None
+        else:
+            hi = (u & ~0x1FFF).view(torch.float32)
+            lo = (wp - hi).view(K, nq, 4, npad).permute(0, 1, 3, 2).contiguous()
+        hi = hi.view(K, nq, 4, npad).permute(0, 1, 3, 2).contiguous()
+        if len(_UMMA_CACHE) > 4096:
+            _UMMA_CACHE.clear()
+        hit = _UMMA_CACHE[key] = (hi, lo, npad, W)   # keep W alive so the data_ptr key stays unique
+    return hit[0], hit[1], hit[2]
+
+
 def spconv(x, cin, nbr, W, cout, bias=None, m_out=None, want_stats=False, out=None, out_col=0):
     """out[j,:cout] = bias + sum_k W[k]^T x[nbr[j,k], :cin].  x [*, ld]; W [K, cin, ceil4(cout)] prepared by the
     module.  Returns (out [m_out, ceil4(cout)] or view into `out`, bn_partial or None)."""
@@ -260,9 +293,16 @@ def spconv(x, cin, nbr, W, cout, bias=None, m_out=None, want_stats=False, out=No
     _prof_work("spconv", lambda: {"pairs": int((nbr >= 0).sum().item()) if nbr is not None else int(m_out),
                                   "cin": cin, "cout": cout, "K": K, "m_out": int(m_out), "m_in": int(x.shape[0])})
     _e = _prof_begin("spconv")
-    _lib.check(L.ep_spconv_fwd(x.data_ptr(), x.stride(0), cin, _ptr(nbr), K, W.data_ptr(), W.shape[2], cout,
-                               _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
-                               stream_ptr()), "ep_spconv_fwd")
+    if SPCONV_IMPL == "ffma":
+        _lib.check(L.ep_spconv_fwd(x.data_ptr(), x.stride(0), cin, _ptr(nbr), K, W.data_ptr(), W.shape[2], cout,
+                                   _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
+                                   stream_ptr()), "ep_spconv_fwd")
+    else:
+        prec = 3 if SPCONV_IMPL == "tf32x3" else 1
+        w_hi, w_lo, npad = _umma_weights(W, cout, prec)
+        _lib.check(L.ep_spconv_tc_fwd(x.data_ptr(), x.stride(0), cin, _ptr(nbr), K, w_hi.data_ptr(), _ptr(w_lo), npad,
+                                      cout, _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
+                                      prec, stream_ptr()), "ep_spconv_tc_fwd")
     _prof_end(_e)
     return out, part
 

@@ -100,6 +100,11 @@ int ep_devoxelize(const float* feat, int ld_in, int c, const int32_t* idx, const
 int ep_spconv_num_row_tiles(int64_t m_out);
 int ep_spconv_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, int K, const float* W, int ldw, int cout,
                   const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, cudaStream_t stream);
+/* tensor-core variant: tcgen05.mma kind::tf32, fp32 accumulators in TMEM; prec 1 = tf32, 3 = 3xTF32 split (fp32-grade).
+ * w_hi / w_lo: float[K][ceil(cin/4)][npad][4] (see csrc/spconv_tc.cu). */
+int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, int K, const float* w_hi,
+                     const float* w_lo, int npad, int cout, const float* bias, float* out, int ld_out, int64_t m_out,
+                     float* bn_partial, int prec, cudaStream_t stream);
 int ep_colstats(const float* x, int ld, int64_t m, int c, float* bn_partial, cudaStream_t stream);
 int ep_bn_finalize(const float* bn_partial, int num_row_tiles, int c, int64_t m, float eps, const float* gamma,
                    const float* beta, float* scale_shift, float* mean_var, cudaStream_t stream);
