@@ -56,14 +56,19 @@ __global__ void coord_keys_kernel(const int4* __restrict__ coords, int m, int ba
 }
 
 // initial_voxelize front end (ops/torchsparse_utils.py:16-19): new = [C.xyz / vres, b]; key = sphash(floor(new))
-__global__ void point_keys_kernel(const float4* __restrict__ pts, int n, float vres, float4* __restrict__ pts_scaled,
-                                  uint64_t* __restrict__ keys) {
+__global__ void point_keys_kernel(const float4* __restrict__ pts, int n, float vres, int spatial,
+                                  float4* __restrict__ pts_scaled, uint64_t* __restrict__ keys) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     float4 p = pts[i];
     float4 q = make_float4(__fdiv_rn(p.x, vres), __fdiv_rn(p.y, vres), __fdiv_rn(p.z, vres), p.w);
     if (pts_scaled) pts_scaled[i] = q;
-    keys[i] = ep_sphash((int)floorf(q.x), (int)floorf(q.y), (int)floorf(q.z), (int)floorf(q.w));
+    const int x = (int)floorf(q.x), y = (int)floorf(q.y), z = (int)floorf(q.z), b = (int)floorf(q.w);
+    // spatial != 0: packed (b,x,y,z) key -> voxels come out in raster order (gather locality); identical grouping,
+    // only the internal row order differs from the reference's ascending-hash order
+    keys[i] = spatial ? (((uint64_t)(uint16_t)b << 48) | ((uint64_t)(uint16_t)(x + 32768) << 32) |
+                         ((uint64_t)(uint16_t)(y + 32768) << 16) | (uint64_t)(uint16_t)(z + 32768))
+                      : ep_sphash(x, y, z, b);
   }
 }
 
@@ -214,9 +219,11 @@ int ep_coord_keys(const int32_t* coords, int64_t m, int batch_first, uint64_t* k
   return EP_OK;
 }
 
-int ep_point_keys(const float* pts, int64_t n, float vres, float* pts_scaled, uint64_t* keys, cudaStream_t stream) {
+int ep_point_keys(const float* pts, int64_t n, float vres, int spatial, float* pts_scaled, uint64_t* keys,
+                  cudaStream_t stream) {
   if (n <= 0) return EP_ERR_ARG;
-  point_keys_kernel<<<ep_div_up(n, 256), 256, 0, stream>>>((const float4*)pts, (int)n, vres, (float4*)pts_scaled, keys);
+  point_keys_kernel<<<ep_div_up(n, 256), 256, 0, stream>>>((const float4*)pts, (int)n, vres, spatial,
+                                                           (float4*)pts_scaled, keys);
   EP_CHECK_LAUNCH();
   return EP_OK;
 }

@@ -3,12 +3,12 @@
 //     out[j, :] = bias + sum_k W[k]^T . in[nbr[j, k], :]
 //
 // One CTA owns 128 output rows x NT output channels (NT <= 128, multiple of 16).  For every kernel offset with a
-// neighbour in the tile and every 16-channel slab of Cin, all 256 threads gather the A slab (rows through the
+// neighbour in the tile and every 16-channel slab of Cin, 8 producer warps gather the A slab (rows through the
 // neighbour table, 16-byte loads) and copy the matching weight slab into shared memory in the UMMA canonical
-// K-major / no-swizzle layout (8x16B core matrices); one elected thread then issues the MMAs and commits them to an
-// mbarrier, so the gather of slab s+1 overlaps the tensor work of slab s (3-stage ring).  Accumulators never leave
-// TMEM until the epilogue (tcgen05.ld), which adds the bias, stores the rows and emits per-CTA column sums / sums of
-// squares for batch-statistics BatchNorm.
+// K-major / no-swizzle layout (8x16B core matrices); a dedicated issuer thread waits on the slab's full-mbarrier,
+// issues the MMAs and commits them to the slab's empty-mbarrier (4-stage ring, producers run ahead).  Accumulators
+// never leave TMEM until the epilogue (tcgen05.ld), which adds the bias, stores the rows and emits per-CTA column
+// sums / sums of squares for batch-statistics BatchNorm.
 //
 // Precision: kind::tf32 reads the top 19 bits of each fp32 operand.  PREC == 1 rounds both operands to tf32
 // (rel. error 2^-11 per product); PREC == 3 is the error-compensated split  a = a_hi + a_lo, b = b_hi + b_lo,
@@ -20,7 +20,7 @@ namespace {
 
 constexpr int TMR = 128;      // output rows per CTA (UMMA M)
 constexpr int KCT = 16;       // input channels per stage (2 MMAs of K = 8)
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 4;
 constexpr int TC_THREADS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,159 +84,225 @@ __device__ __forceinline__ float tf32_round(float x) {  // round-to-nearest-even
   return __uint_as_float(u & 0xFFFFE000u);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised pipeline: warps 0..7 are PRODUCERS (gather A rows through the neighbour table, split to tf32
+// hi/lo, copy the weight slab; run up to NSTAGE slabs ahead of the tensor core), warp 8 lane 0 is the MMA ISSUER
+// (waits full[s], issues tcgen05.mma, commits to empty[s]).  After the last slab warps 0..7 run the epilogue.
+//
+// Accumulators (PREC == 3): the hi.hi products round-robin over 3 TMEM accumulators and the two cross terms go to a
+// 4th one; they are summed in fp32 registers in the epilogue.  The tensor core adds into its accumulator with
+// truncation, so the error grows with the number of MMAs chained on one accumulator: keeping the (tiny) cross terms
+// off the main chain and splitting it three ways brings the result back to fp32-FMA grade.
 template <int PREC>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS + 32)
 spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*/, const int* __restrict__ nbr, int K,
                  const float* __restrict__ w_hi, const float* __restrict__ w_lo, int nq /*ceil(cin/4)*/,
                  int npad /*total padded cout*/, int nt /*columns of this launch's tile*/, int tmem_cols, int cout,
                  const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m_out,
                  float* __restrict__ bn_partial, int bn_rows) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // per stage: A_hi [4][128][4 floats] (8 KB) | A_lo (8 KB, PREC==3) | B_hi [4][nt][4] | B_lo
+  constexpr int NACC = PREC == 3 ? 4 : 1;
   const int a_bytes = (KCT / 4) * TMR * 16;
   const int b_bytes = (KCT / 4) * nt * 16;
   const int stage_bytes = (PREC == 3 ? 2 : 1) * (a_bytes + b_bytes);
-  __shared__ uint64_t mma_done[NSTAGE];
+  int* s_nbr = reinterpret_cast<int*>(smem_raw + (size_t)NSTAGE * stage_bytes);  // [K][128] neighbour rows of the tile
+  __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE];
   __shared__ uint64_t all_done;
   __shared__ uint32_t tmem_base_s;
-  __shared__ int s_nbr[TMR];
-  __shared__ int s_any;
+  __shared__ int s_klist[32];
+  __shared__ int s_nk;
   __shared__ float s_red[8][128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TMR;
   const int col0 = blockIdx.y * nt;
+  const bool producer = warp < 8;
 
-  if (warp == 0) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (tid == 32) {
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(&mma_done[s], 1);
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 8); mbar_init(&empty_bar[s], 1); }
     mbar_init(&all_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the tile's neighbour table, transposed to [k][row] (coalesced global read, conflict-free smem use)
+  for (int e = tid; e < TMR * K; e += blockDim.x) {
+    const int r = e / K, k = e - r * K;
+    const int j = row0 + r;
+    int v = -1;
+    if (j < m_out) v = nbr ? nbr[(size_t)j * K + k] : j;
+    s_nbr[k * TMR + r] = v;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = tmem_base_s;
-  // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(TMR >> 4) << 24);
-
-  const int nchunk = (cin4 + KCT - 1) / KCT;
-  int it = 0;  // pipeline slot counter (uniform across the CTA)
-  for (int k = 0; k < K; ++k) {
-    __syncthreads();
-    if (tid == 0) s_any = 0;
-    __syncthreads();
-    if (tid < TMR) {
-      const int j = row0 + tid;
-      int r = -1;
-      if (j < m_out) r = nbr ? nbr[(size_t)j * K + k] : j;
-      s_nbr[tid] = r;
-      if (r >= 0) s_any = 1;
+  // kernel offsets with at least one neighbour in the tile
+  if (warp == 0) {
+    int nk = 0;
+    for (int k = 0; k < K; ++k) {
+      int any = 0;
+      for (int r = lane; r < TMR; r += 32) any |= (s_nbr[k * TMR + r] >= 0);
+      if (__any_sync(0xffffffffu, any)) { if (lane == 0) s_klist[nk] = k; ++nk; }
     }
-    __syncthreads();
-    if (!s_any) continue;
-    for (int c = 0; c < nchunk; ++c, ++it) {
-      const int stage = it % NSTAGE;
-      if (it >= NSTAGE) mbar_wait(&mma_done[stage], ((it / NSTAGE) - 1) & 1);  // MMAs that read this stage retired
+    if (lane == 0) s_nk = nk;
+  }
+  __syncthreads();
+  const uint32_t tmem_d = tmem_base_s;
+  const int nk = s_nk;
+  const int nchunk = (cin4 + KCT - 1) / KCT;
+  const int T = nk * nchunk;  // pipeline slabs of this CTA
+
+  if (producer) {
+    // ---------------------------------------------------------------- producers
+    const int rowA = tid & (TMR - 1), jq0 = tid >> 7;            // items (rowA, jq0) and (rowA, jq0 + 2)
+    const int nb_items = (KCT / 4) * nt;                         // float4 items of the weight slab
+    float4 a_reg[2], bh_reg[2], bl_reg[2];
+    // loop-invariant parts of this thread's two weight-slab items
+    int b_jq[2], b_n[2];
+    bool b_on[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = tid + i * TC_THREADS;
+      b_on[i] = e < nb_items;
+      b_jq[i] = b_on[i] ? e / nt : 0;
+      b_n[i] = b_on[i] ? e - b_jq[i] * nt : 0;
+    }
+    int ld_ki = 0, ld_c = 0;  // (active-offset index, channel slab) of the next slab to load
+    auto issue_loads = [&]() {
+      const int k = s_klist[ld_ki], c = ld_c;
+      const int src = s_nbr[k * TMR + rowA];
+      const float* arow = in + (size_t)src * ld_in + c * KCT;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int colq = (jq0 + 2 * i) * 4;
+        a_reg[i] = (src >= 0 && c * KCT + colq < cin4) ? __ldg(reinterpret_cast<const float4*>(arow + colq))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const size_t wbase = ((size_t)k * nq + (size_t)c * (KCT / 4)) * npad + col0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        bh_reg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bl_reg[i] = bh_reg[i];
+        if (b_on[i] && c * (KCT / 4) + b_jq[i] < nq) {
+          const size_t off = (wbase + (size_t)b_jq[i] * npad + b_n[i]) * 4;
+          bh_reg[i] = __ldg(reinterpret_cast<const float4*>(w_hi + off));
+          if (PREC == 3) bl_reg[i] = __ldg(reinterpret_cast<const float4*>(w_lo + off));
+        }
+      }
+      if (++ld_c == nchunk) { ld_c = 0; ++ld_ki; }
+    };
+    if (T > 0) issue_loads();
+    for (int t = 0; t < T; ++t) {
+      const int stage = t % NSTAGE;
+      float4 a_cur[2] = {a_reg[0], a_reg[1]};
+      float4 bh_cur[2] = {bh_reg[0], bh_reg[1]}, bl_cur[2] = {bl_reg[0], bl_reg[1]};
+      if (t + 1 < T) issue_loads();                               // next slab's loads fly while this one is stored
+      if (t >= NSTAGE) mbar_wait(&empty_bar[stage], ((t / NSTAGE) - 1) & 1);
       uint8_t* sbase = smem_raw + (size_t)stage * stage_bytes;
       float4* a_hi = reinterpret_cast<float4*>(sbase);
       float4* a_lo = reinterpret_cast<float4*>(sbase + a_bytes);
       float4* b_hi = reinterpret_cast<float4*>(sbase + (PREC == 3 ? 2 : 1) * a_bytes);
       float4* b_lo = reinterpret_cast<float4*>(sbase + (PREC == 3 ? 2 : 1) * a_bytes + b_bytes);
-      // ---- gather A: 4 chunks x 128 rows of 16 B; consecutive threads -> consecutive rows (conflict-free STS)
 #pragma unroll
-      for (int i = 0; i < (KCT / 4) * TMR / TC_THREADS; ++i) {
-        const int e = tid + i * TC_THREADS;
-        const int row = e & (TMR - 1), jq = e >> 7;
-        const int col = c * KCT + jq * 4;
-        const int src = s_nbr[row];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src >= 0 && col < cin4) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)src * ld_in + col));
-        if (PREC == 3) {
-          float4 h = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
-                                 __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-          a_hi[jq * TMR + row] = h;
-          a_lo[jq * TMR + row] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        } else {
-          a_hi[jq * TMR + row] = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
-        }
+      for (int i = 0; i < 2; ++i) {
+        const float4 v = a_cur[i];
+        const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+        a_hi[(jq0 + 2 * i) * TMR + rowA] = h;
+        if (PREC == 3) a_lo[(jq0 + 2 * i) * TMR + rowA] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
-      // ---- weights: [k][q][npad][4] -> B stage [4][nt][4]; contiguous 16-byte copies
-      for (int e = tid; e < (KCT / 4) * nt; e += TC_THREADS) {
-        const int jq = e / nt, n = e - jq * nt;
-        const int q = c * (KCT / 4) + jq;
-        float4 vh = make_float4(0.f, 0.f, 0.f, 0.f), vl = vh;
-        if (q < nq) {
-          const size_t off = (((size_t)k * nq + q) * npad + col0 + n) * 4;
-          vh = __ldg(reinterpret_cast<const float4*>(w_hi + off));
-          if (PREC == 3) vl = __ldg(reinterpret_cast<const float4*>(w_lo + off));
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (b_on[i]) {
+          b_hi[tid + i * TC_THREADS] = bh_cur[i];
+          if (PREC == 3) b_lo[tid + i * TC_THREADS] = bl_cur[i];
         }
-        b_hi[e] = vh;
-        if (PREC == 3) b_lo[e] = vl;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy STS -> visible to the tensor core
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
-#pragma unroll
-        for (int kk = 0; kk < KCT / 8; ++kk) {
-          const uint32_t a_off = kk * 2 * TMR * 16, b_off = kk * 2 * nt * 16;
-          const uint64_t dah = umma_desc(sa_hi + a_off, TMR * 16, 128), dbh = umma_desc(sb_hi + b_off, nt * 16, 128);
-          umma_tf32(tmem_d, dah, dbh, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-          if (PREC == 3) {
-            const uint64_t dal = umma_desc(sa_lo + a_off, TMR * 16, 128), dbl = umma_desc(sb_lo + b_off, nt * 16, 128);
-            umma_tf32(tmem_d, dal, dbh, idesc, 1u);
-            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-          }
-        }
-        umma_commit(&mma_done[stage]);  // arrives when the MMAs issued so far have finished reading smem
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
     }
+  } else if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (one thread)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(TMR >> 4) << 24);
+    uint32_t used = 0;  // bit a: accumulator a already written
+    for (int t = 0; t < T; ++t) {
+      const int stage = t % NSTAGE;
+      mbar_wait(&full_bar[stage], (t / NSTAGE) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sbase = smem_u32(smem_raw + (size_t)stage * stage_bytes);
+      const uint32_t sa_hi = sbase, sa_lo = sbase + a_bytes;
+      const uint32_t sb_hi = sbase + (PREC == 3 ? 2 : 1) * a_bytes, sb_lo = sb_hi + b_bytes;
+#pragma unroll
+      for (int kk = 0; kk < KCT / 8; ++kk) {
+        const uint32_t a_off = kk * 2 * TMR * 16, b_off = kk * 2 * nt * 16;
+        const uint64_t dah = umma_desc(sa_hi + a_off, TMR * 16, 128), dbh = umma_desc(sb_hi + b_off, nt * 16, 128);
+        const int am = (PREC == 3) ? ((t * (KCT / 8) + kk) % 3) : 0;
+        umma_tf32(tmem_d + am * nt, dah, dbh, idesc, (used >> am) & 1u);
+        used |= 1u << am;
+        if (PREC == 3) {
+          const uint64_t dal = umma_desc(sa_lo + a_off, TMR * 16, 128), dbl = umma_desc(sb_lo + b_off, nt * 16, 128);
+          umma_tf32(tmem_d + 3 * nt, dal, dbh, idesc, (used >> 3) & 1u);
+          used |= 1u << 3;
+          umma_tf32(tmem_d + 3 * nt, dah, dbl, idesc, 1u);
+        }
+      }
+      umma_commit(&empty_bar[stage]);  // arrives once the MMAs above have finished reading this stage
+    }
+    umma_commit(&all_done);
+    // tell the epilogue which accumulators hold data
+    s_klist[31] = (int)used;
   }
-  // ---- all MMAs done?
-  if (tid == 0) umma_commit(&all_done);
   __syncthreads();
-  if (it > 0) mbar_wait(&all_done, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-  // ---- epilogue: warp w reads TMEM lanes [32*(w%4), +32) and columns of half (w/4)
-  const int q = warp & 3, half = warp >> 2;
-  const int row = row0 + q * 32 + lane;
-  const int ncol_half = (nt / 16 + 1) / 2 * 16;  // columns handled by half 0 (multiple of 16)
-  const int cbeg = half == 0 ? 0 : ncol_half, cend = half == 0 ? min(ncol_half, nt) : nt;
-  for (int cb = cbeg; cb < cend; cb += 16) {
-    float v[16];
-    if (it > 0) tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
-    else {
+  if (producer) {
+    // ---------------------------------------------------------------- epilogue (warps 0..7)
+    if (T > 0) mbar_wait(&all_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t used = (uint32_t)s_klist[31];
+    const int q = warp & 3, half = warp >> 2;
+    const int row = row0 + q * 32 + lane;
+    const int ncol_half = (nt / 16 + 1) / 2 * 16;
+    const int cbeg = half == 0 ? 0 : ncol_half, cend = half == 0 ? min(ncol_half, nt) : nt;
+    for (int cb = cbeg; cb < cend; cb += 16) {
+      float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = 0.f;
-    }
-    float s[16], sq[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int col = col0 + cb + i;
-      const float val = v[i] + ((bias && col < cout) ? bias[col] : 0.f);
-      const bool ok = row < m_out && col < cout;
-      if (ok) out[(size_t)row * ld_out + col] = val;
-      s[i] = ok ? val : 0.f;
-      sq[i] = ok ? val * val : 0.f;
-    }
-    if (bn_partial) {
+      for (int a = 0; a < NACC; ++a) {
+        if (T > 0 && ((used >> a) & 1u)) {
+          float t16[16];
+          tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * nt + cb), t16);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          s[i] += __shfl_xor_sync(0xffffffffu, s[i], d);
-          sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], d);
+          for (int i = 0; i < 16; ++i) v[i] += t16[i];
         }
       }
-      if (lane == 0) {
+      float s[16], sq[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { s_red[q][cb + i] = s[i]; s_red[4 + q][cb + i] = sq[i]; }
+      for (int i = 0; i < 16; ++i) {
+        const int col = col0 + cb + i;
+        const float val = v[i] + ((bias && col < cout) ? bias[col] : 0.f);
+        const bool ok = row < m_out && col < cout;
+        if (ok) out[(size_t)row * ld_out + col] = val;
+        s[i] = ok ? val : 0.f;
+        sq[i] = ok ? val * val : 0.f;
+      }
+      if (bn_partial) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], d);
+            sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], d);
+          }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { s_red[q][cb + i] = s[i]; s_red[4 + q][cb + i] = sq[i]; }
+        }
       }
     }
   }
@@ -257,7 +323,7 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
       }
     }
   }
-  if (warp == 0) {
+  if (warp == 8) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols));
   }
 }
@@ -289,9 +355,11 @@ int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, in
     if (npad % 128 != 0) return EP_ERR_ARG;
     nt = 128;
   }
-  const int tmem_cols = pow2_cols(nt);
+  if (K > 27) return EP_ERR_UNSUPPORTED;
+  const int tmem_cols = pow2_cols((prec == 3 ? 4 : 1) * nt);
+  if (tmem_cols > 512) return EP_ERR_UNSUPPORTED;
   const size_t stage = (size_t)(prec == 3 ? 2 : 1) * ((KCT / 4) * TMR * 16 + (KCT / 4) * nt * 16);
-  const size_t smem = stage * NSTAGE;
+  const size_t smem = stage * NSTAGE + (size_t)K * TMR * sizeof(int);
   cudaError_t e;
   if (prec == 3) e = cudaFuncSetAttribute(spconv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   else e = cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -299,10 +367,10 @@ int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, in
   dim3 grid(ep_div_up(m_out, TMR), npad / nt);
   const int bn_rows = ep_div_up(m_out, 64);
   if (prec == 3)
-    spconv_tc_kernel<3><<<grid, TC_THREADS, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, (cin + 3) / 4, npad, nt,
+    spconv_tc_kernel<3><<<grid, TC_THREADS + 32, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, (cin + 3) / 4, npad, nt,
                                                            tmem_cols, cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows);
   else
-    spconv_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, (cin + 3) / 4, npad, nt,
+    spconv_tc_kernel<1><<<grid, TC_THREADS + 32, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, (cin + 3) / 4, npad, nt,
                                                            tmem_cols, cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows);
   EP_CHECK_LAUNCH();
   return EP_OK;

@@ -197,7 +197,7 @@ class GRUFusion(nn.Module):
                 r_coords = ops.aligned_coords(upd0, org, voxel_size, w2ac, zero_batch=True)
                 gru_v, gru_i = self.fusion_nets_voxel[scale], self.fusion_nets_img[scale]
                 pc1 = sparse.PointCloud(r_coords, gru_v.vres)
-                pc2 = sparse.PointCloud(pc1.scaled, gru_v.vres)
+                pc2 = sparse.PointCloud(pc1.scaled, gru_v.vres, order="hash")
                 out_v = gru_v.run(gvalues[:, :cv], values[:, :cv], pc1, pc2)
                 out_i = gru_i.run(gvalues[:, cv:c_all], values[:, cv:c_all], pc1, pc2)
                 values = torch.cat([out_v[:, :cv], out_i[:, :c_all - cv]], dim=-1)

@@ -221,8 +221,7 @@ class SConv3d(nn.Module):
         inc, outc = self.net.inc, self.net.outc
         x = pc.voxelize(feat, inc)
         y, _ = ops.spconv(x, inc, pc.vox.kmap_k3(), self.net.prepared(), outc)
-        src = taps_pc if taps_pc is not None else pc
-        idx, w = src.taps(src.vox)
+        idx, w = taps_pc.taps_in_hash_order() if taps_pc is not None else pc.taps(pc.vox)
         lin, _ = linear(feat, self.point_transforms[0], self._pl)
         return sparse.devoxelize(y, outc, idx, w, add=lin)
 
@@ -272,7 +271,7 @@ class ConvGRU(nn.Module):
     def forward(self, h, x):
         pts = h.C.float().contiguous()
         pc1 = sparse.PointCloud(pts, self.vres)
-        pc2 = sparse.PointCloud(pc1.scaled, self.vres)
+        pc2 = sparse.PointCloud(pc1.scaled, self.vres, order="hash")
         out = self.run(h.F.contiguous(), x.F.contiguous(), pc1, pc2)
         h.F = out[:, :self.hidden_dim]
         return h.F

@@ -261,12 +261,10 @@ def _umma_weights(W, cout, prec):
         wp = torch.zeros((K, nq * 4, npad), dtype=torch.float32, device=W.device)
         wp[:, :cin, :cout] = W[:, :, :cout]
         u = wp.view(torch.int32)
-        if prec == 1:
-            hi = ((u + 0xFFF + ((u >> 13) & 1)) & ~0x1FFF).view(torch.float32)
-            lo = None
-        else:
-            hi = (u & ~0x1FFF).view(torch.float32)
-            lo = (wp - hi).view(K, nq, 4, npad).permute(0, 1, 3, 2).contiguous()
+        hi = ((u + 0xFFF + ((u >> 13) & 1)) & ~0x1FFF).view(torch.float32)     # round-to-nearest-even tf32
+        lo = None
+        if prec == 3:
+            lo = (wp - hi).view(K, nq, 4, npad).permute(0, 1, 3, 2).contiguous()  # exact remainder
         hi = hi.view(K, nq, 4, npad).permute(0, 1, 3, 2).contiguous()
         if len(_UMMA_CACHE) > 4096:
             _UMMA_CACHE.clear()
@@ -293,7 +291,7 @@ def spconv(x, cin, nbr, W, cout, bias=None, m_out=None, want_stats=False, out=No
     _prof_work("spconv", lambda: {"pairs": int((nbr >= 0).sum().item()) if nbr is not None else int(m_out),
                                   "cin": cin, "cout": cout, "K": K, "m_out": int(m_out), "m_in": int(x.shape[0])})
     _e = _prof_begin("spconv")
-    if SPCONV_IMPL == "ffma":
+    if SPCONV_IMPL == "ffma" or K == 1:   # dense per-row linears (2 slabs) stay on the CUDA-core GEMM: no gather to hide
         _lib.check(L.ep_spconv_fwd(x.data_ptr(), x.stride(0), cin, _ptr(nbr), K, W.data_ptr(), W.shape[2], cout,
                                    _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
                                    stream_ptr()), "ep_spconv_fwd")

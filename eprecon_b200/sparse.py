@@ -68,25 +68,30 @@ class VoxelSet:
 class PointCloud:
     """Points + their stride-1 voxelisation (initial_voxelize, ops/torchsparse_utils.py:15-35)."""
 
-    def __init__(self, pts, vres):
-        """pts float32 [N,4]=(x,y,z,b) in metres (aligned-camera frame); vres = voxel resolution."""
+    def __init__(self, pts, vres, order="spatial"):
+        """pts float32 [N,4]=(x,y,z,b) in metres (aligned-camera frame); vres = voxel resolution.
+        order: "spatial" = voxel rows in (b,x,y,z) raster order (neighbour gathers stay cache-local; every consumer is
+        order-independent), "hash" = the reference's ascending-sphash order (torch.unique of the hashes), needed only
+        where the reference's ConvGRU.convr quirk makes the row order observable."""
         dev = pts.device
         L = _L()
         n = pts.shape[0]
         self.n = n
         self.scaled = torch.empty_like(pts)
         keys = torch.empty(n, dtype=torch.int64, device=dev)
-        _lib.check(L.ep_point_keys(pts.data_ptr(), n, float(vres), self.scaled.data_ptr(), keys.data_ptr(), stream_ptr()),
-                   "ep_point_keys")
-        seg = ops.sort_segments(keys, 60)
+        spatial = order == "spatial"
+        _lib.check(L.ep_point_keys(pts.data_ptr(), n, float(vres), int(spatial), self.scaled.data_ptr(), keys.data_ptr(),
+                                   stream_ptr()), "ep_point_keys")
+        seg = ops.sort_segments(keys, 64 if spatial else 60)
         self.csr1 = (seg["perm"], seg["seg_start"], seg["seg_end"])
         self.idx_query = seg["seg_of_item"]
         m = seg["S"]
         vox = torch.empty((m, 4), dtype=torch.int32, device=dev)
         _lib.check(L.ep_segment_coords(self.scaled.data_ptr(), seg["perm"].data_ptr(), seg["seg_start"].data_ptr(), m,
                                        vox.data_ptr(), stream_ptr()), "ep_segment_coords")
-        uniq_keys = seg["keys_sorted"][seg["seg_start"].long()]
-        self.vox = VoxelSet(vox, 1, keys=uniq_keys)
+        self.vox = VoxelSet(vox, 1, keys=None if spatial else seg["keys_sorted"][seg["seg_start"].long()])
+        self.order = order
+        self._hash_rank = None
         self._taps = {}
         self._csr = {1: self.csr1}
 
@@ -109,6 +114,20 @@ class PointCloud:
                                              stream_ptr()), "ep_devox_prepare")
             self._taps[vset.stride] = (idx, w)
         return self._taps[vset.stride]
+
+    def taps_in_hash_order(self):
+        """Stride-1 taps with the voxel ids translated to the reference's ascending-hash row order (what the reference's
+        cached idx_query holds when ConvGRU.convr reuses convz's taps on a different voxel list)."""
+        idx, w = self.taps(self.vox)
+        if self.order == "hash":
+            return idx, w
+        if self._hash_rank is None:
+            seg = ops.sort_segments(ops.coord_keys(self.vox.coords, batch_first=False), 60)
+            rank = seg["seg_of_item"]                       # hash rank of every (spatially ordered) voxel row
+            flat = idx.view(-1).long()
+            tr = torch.where(flat >= 0, rank[flat.clamp_min(0)], torch.full_like(flat, -1, dtype=torch.int32))
+            self._hash_rank = tr.view(-1, 8).contiguous()
+        return self._hash_rank, w
 
     def csr_for(self, vset):
         """CSR of points by voxel of `vset` (point_to_voxel, ops/torchsparse_utils.py:40-63); points whose cell is

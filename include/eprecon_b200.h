@@ -71,7 +71,8 @@ int ep_sort_segments(const uint64_t* keys, int64_t n, int key_bits, uint64_t sen
 int ep_hash_build(const uint64_t* keys, int64_t m, uint64_t* table_keys, int32_t* table_vals, int64_t capacity,
                   cudaStream_t stream);
 int ep_coord_keys(const int32_t* coords, int64_t m, int batch_first, uint64_t* keys, cudaStream_t stream);
-int ep_point_keys(const float* pts, int64_t n, float vres, float* pts_scaled, uint64_t* keys, cudaStream_t stream);
+int ep_point_keys(const float* pts, int64_t n, float vres, int spatial, float* pts_scaled, uint64_t* keys,
+                  cudaStream_t stream);
 int ep_segment_coords(const float* pts_scaled, const int32_t* perm, const int32_t* seg_start, int64_t m,
                       int32_t* vox_coords, cudaStream_t stream);
 int ep_kmap_build(const int32_t* out_coords, int64_t m_out, int batch_first, const int32_t* offsets, int K,

@@ -35,7 +35,7 @@ def test_voxelize_taps_and_maps(cuda_lib):
     pts = shell_points()
     feat = torch.randn(len(pts), 12, generator=torch.Generator().manual_seed(1))
     st, scaled, iq, cnt = restate.voxelize_points(feat, pts, 0.16)
-    pc = sparse.PointCloud(pts.cuda(), 0.16)
+    pc = sparse.PointCloud(pts.cuda(), 0.16, order="hash")
     assert torch.equal(pc.vox.coords.cpu(), st.C)                       # same voxels in the same (hash-sorted) order
     assert torch.equal(pc.idx_query.cpu().long(), iq)
     assert torch.equal(pc.scaled.cpu(), scaled)
@@ -64,7 +64,7 @@ def test_sparse_conv_k3_and_strided(cuda_lib, cin, cout):
     g = torch.Generator().manual_seed(cin * 131 + cout)
     feat = torch.randn(len(pts), cin, generator=g)
     st, scaled, _, _ = restate.voxelize_points(feat, pts, 0.16)
-    pc = sparse.PointCloud(pts.cuda(), 0.16)
+    pc = sparse.PointCloud(pts.cuda(), 0.16, order="hash")
     fpad = torch.zeros(len(pts), ops.ceil4(cin))
     fpad[:, :cin] = feat
     x = pc.voxelize(fpad.cuda(), cin)

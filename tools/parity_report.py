@@ -1,0 +1,59 @@
+"""Per-stage parity report of the CUDA path against the CPU oracle on the small golden configuration, for every
+sparse-conv implementation (fp32 FFMA, tcgen05 3xTF32, tcgen05 TF32).  Prints one JSON line per implementation."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from eprecon_b200 import ops, synth  # noqa: E402
+from eprecon_b200.neucon_network import NeuConNet  # noqa: E402
+from oracle import restate  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def main():
+    g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "neucon_small.npz"))
+    n_vox = tuple(int(v) for v in g["n_vox"])
+    cfg = synth.make_cfg(n_vox=n_vox)
+    cfg.THRESHOLDS = [float(v) for v in g["thresholds"]]
+    net = NeuConNet(cfg)
+    sd = synth.synthetic_state_dict(net, 1)
+    inputs, fa, fb = synth.make_fragment(seed=1, image_hw=(240, 320), n_vox=n_vox)
+    ot = {}
+    with torch.no_grad():
+        oout = restate.neucon_forward(sd, cfg, fa, fb, inputs, restate.FusionState(), trace=ot)
+    net = net.cuda()
+    cin = {k: (v.cuda() if torch.is_tensor(v) else ([t.cuda() for t in v] if isinstance(v, list) and torch.is_tensor(v[0]) else v))
+           for k, v in inputs.items()}
+    fa_c, fb_c = [[t.cuda() for t in f] for f in fa], [[t.cuda() for t in f] for f in fb]
+    for impl in ("ffma", "tf32x3", "tf32"):
+        ops.SPCONV_IMPL = impl
+        cin["scene"] = [f"scene_{impl}"]
+        net.trace, net.teacher = {}, ot
+        out, _ = net(fa_c, fb_c, cin, {})
+        t = net.trace
+        rep = {"impl": impl, "init_occ": rel(t["init"]["occ"], ot["init"]["occ"])}
+        for lv in range(3):
+            a, b = t[f"l{lv}_pre_gru"], ot[f"l{lv}_pre_gru"]
+            rep[f"l{lv}_coords_exact"] = bool(torch.equal(a["coords"].cpu(), b["coords"].int()))
+            rep[f"l{lv}_spvcnn"] = rel(a["spvcnn"], b["spvcnn"])
+            a, b = t[f"l{lv}"], ot[f"l{lv}"]
+            rep[f"l{lv}_union_exact"] = bool(torch.equal(a["coords"].cpu().long(), b["coords"]))
+            rep[f"l{lv}_gru"] = rel(a["feat_all"], b["feat_all"])
+            rep[f"l{lv}_tsdf"] = rel(a["tsdf"], b["tsdf"])
+            rep[f"l{lv}_occ"] = rel(a["occ"], b["occ"])
+            rep[f"l{lv}_mask_flips"] = int((a["occupancy"].cpu() != b["occupancy"]).sum())
+        rep["final_coords_exact"] = bool(torch.equal(out["coords"].cpu(), oout["coords"]))
+        rep["final_tsdf"] = rel(out["tsdf"], oout["tsdf"])
+        print(json.dumps(rep))
+
+
+if __name__ == "__main__":
+    main()
