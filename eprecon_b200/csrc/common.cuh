@@ -77,3 +77,36 @@ __host__ __device__ __forceinline__ uint64_t ep_mix64(uint64_t k) {
 }
 
 #define EP_HASH_EMPTY 0xFFFFFFFFFFFFFFFFULL
+
+// 3-D Morton (Z-order) key of three 16-bit coordinates (offset by 32768 to make them unsigned), batch in the top 16 bits.
+// Sorting voxels by this key makes every run of 128 consecutive rows a compact blob, so the 27-neighbour gathers of a
+// conv tile stay inside a small, L1-resident window of the feature matrix.
+__host__ __device__ __forceinline__ uint64_t ep_spread3(uint32_t v) {  // 16 bits -> every third bit
+  uint64_t x = v & 0xFFFFu;
+  x = (x | (x << 32)) & 0x00FF00000000FFFFULL;
+  x = (x | (x << 16)) & 0x00FF0000FF0000FFULL;
+  x = (x | (x << 8)) & 0xF00F00F00F00F00FULL;
+  x = (x | (x << 4)) & 0x30C30C30C30C30C3ULL;
+  x = (x | (x << 2)) & 0x9249249249249249ULL;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t ep_compact3(uint64_t x) {
+  x &= 0x9249249249249249ULL;
+  x = (x | (x >> 2)) & 0x30C30C30C30C30C3ULL;
+  x = (x | (x >> 4)) & 0xF00F00F00F00F00FULL;
+  x = (x | (x >> 8)) & 0x00FF0000FF0000FFULL;
+  x = (x | (x >> 16)) & 0x00FF00000000FFFFULL;
+  x = (x | (x >> 32)) & 0xFFFFULL;
+  return (uint32_t)x;
+}
+__host__ __device__ __forceinline__ uint64_t ep_morton_key(int x, int y, int z, int b) {
+  return ((uint64_t)(uint16_t)b << 48) | (ep_spread3((uint32_t)(x + 32768)) << 2) | (ep_spread3((uint32_t)(y + 32768)) << 1) |
+         ep_spread3((uint32_t)(z + 32768));
+}
+__host__ __device__ __forceinline__ void ep_morton_unkey(uint64_t k, int& x, int& y, int& z, int& b) {
+  b = (int)(k >> 48);
+  const uint64_t m = k & 0x0000FFFFFFFFFFFFULL;
+  x = (int)ep_compact3(m >> 2) - 32768;
+  y = (int)ep_compact3(m >> 1) - 32768;
+  z = (int)ep_compact3(m) - 32768;
+}

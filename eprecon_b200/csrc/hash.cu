@@ -64,11 +64,9 @@ __global__ void point_keys_kernel(const float4* __restrict__ pts, int n, float v
     float4 q = make_float4(__fdiv_rn(p.x, vres), __fdiv_rn(p.y, vres), __fdiv_rn(p.z, vres), p.w);
     if (pts_scaled) pts_scaled[i] = q;
     const int x = (int)floorf(q.x), y = (int)floorf(q.y), z = (int)floorf(q.z), b = (int)floorf(q.w);
-    // spatial != 0: packed (b,x,y,z) key -> voxels come out in raster order (gather locality); identical grouping,
-    // only the internal row order differs from the reference's ascending-hash order
-    keys[i] = spatial ? (((uint64_t)(uint16_t)b << 48) | ((uint64_t)(uint16_t)(x + 32768) << 32) |
-                         ((uint64_t)(uint16_t)(y + 32768) << 16) | (uint64_t)(uint16_t)(z + 32768))
-                      : ep_sphash(x, y, z, b);
+    // spatial != 0: Morton key -> voxels come out in Z-order (gather locality); identical grouping, only the internal
+    // row order differs from the reference's ascending-hash order
+    keys[i] = spatial ? ep_morton_key(x, y, z, b) : ep_sphash(x, y, z, b);
   }
 }
 
@@ -118,8 +116,8 @@ __global__ void down_keys_kernel(const int4* __restrict__ coords, int m, int ste
     int x = (int)truncf(__fdiv_rn((float)c.x, (float)step)) * step;
     int y = (int)truncf(__fdiv_rn((float)c.y, (float)step)) * step;
     int z = (int)truncf(__fdiv_rn((float)c.z, (float)step)) * step;
-    keys[i] = ((uint64_t)(uint16_t)c.w << 48) | ((uint64_t)(uint16_t)(x + 32768) << 32) |
-              ((uint64_t)(uint16_t)(y + 32768) << 16) | (uint64_t)(uint16_t)(z + 32768);
+    // (the reference sorts the coarse sites by (b,x,y,z); the order is internal, Z-order keeps conv tiles compact)
+    keys[i] = ep_morton_key(x, y, z, c.w);
   }
 }
 
@@ -127,9 +125,9 @@ __global__ void unpack_down_keys_kernel(const uint64_t* __restrict__ keys_sorted
                                         int m, int4* __restrict__ coords) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < m) {
-    uint64_t k = keys_sorted[seg_start[s]];
-    coords[s] = make_int4((int)((k >> 32) & 0xffff) - 32768, (int)((k >> 16) & 0xffff) - 32768,
-                          (int)(k & 0xffff) - 32768, (int)(k >> 48));
+    int x, y, z, b;
+    ep_morton_unkey(keys_sorted[seg_start[s]], x, y, z, b);
+    coords[s] = make_int4(x, y, z, b);
   }
 }
 

@@ -39,6 +39,7 @@ class GRUFusion(nn.Module):
         self.global_volume = [None, None, None]      # dict(C int32 [Ng,3] global voxel ids, F fp32 [Ng,C])
         self.target_tsdf_volume = [None, None, None]
         self.return_int32 = False
+        self._consts = {}
         if direct_substitute:
             self.fusion_nets_voxel = self.fusion_nets_img = None
         else:
@@ -50,6 +51,17 @@ class GRUFusion(nn.Module):
             for i, ch in enumerate(self.ch_img):
                 self.fusion_nets_img.append(ConvGRU(hidden_dim=ch, input_dim=ch, pres=1,
                                                     vres=self.cfg.VOXEL_SIZE * 2 ** (self.n_scales - i)))
+
+    def _const(self, values, device, dtype):
+        """Small constant device tensors (volume dims, relative origins) cached per value: a torch.tensor(list) H2D copy
+        is a synchronising 200 us detour on the hot path."""
+        key = (values, str(device), dtype)
+        t = self._consts.get(key)
+        if t is None:
+            if len(self._consts) > 256:
+                self._consts.clear()
+            t = self._consts[key] = torch.tensor(values, dtype=dtype, device=device)
+        return t
 
     def reset(self, i, device="cuda"):
         c = self.ch_in[i]
@@ -102,8 +114,8 @@ class GRUFusion(nn.Module):
         coords_t = torch.nonzero(occ_t)
         tgt = self.target_tsdf_volume[scale]
         dev = occ_t.device
-        dim = torch.tensor(dims, device=dev)
-        relt = torch.tensor(rel, device=dev)
+        dim = self._const(tuple(dims), dev, torch.int64)
+        relt = self._const(tuple(rel), dev, torch.int64)
         gc = tgt["C"] - relt
         valid_t = ((gc < dim) & (gc >= 0)).all(dim=-1)
         cc = torch.cat([gc[valid_t], coords_t])[:, :3]
@@ -202,7 +214,7 @@ class GRUFusion(nn.Module):
                 out_i = gru_i.run(gvalues[:, cv:c_all], values[:, cv:c_all], pc1, pc2)
                 values = torch.cat([out_v[:, :cv], out_i[:, :c_all - cv]], dim=-1)
             # update_map (gru_fusion.py:195-204): drop in-volume global rows, append the fused ones
-            relt = torch.tensor(rel, dtype=torch.int32, device=dev)
+            relt = self._const(tuple(rel), dev, torch.int32)
             vpad = values if values.shape[1] == g["F"].shape[1] else torch.nn.functional.pad(
                 values, (0, g["F"].shape[1] - values.shape[1]))
             g["F"] = torch.cat([g["F"][valid == False], vpad])  # noqa: E712

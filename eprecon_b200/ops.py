@@ -35,8 +35,16 @@ def _prof_work(kind, fn):
         PROFILE.setdefault(kind + "_work", []).append(fn())
 
 
+_DEV_INDEX = None
+
+
 def stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream.  torch.cuda.current_stream() costs ~13 us of Python per call (it was
+    7 ms of an 800-launch step); the raw query is ~0.3 us.  One process drives one GPU, so the device index is cached."""
+    global _DEV_INDEX
+    if _DEV_INDEX is None:
+        _DEV_INDEX = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(_DEV_INDEX)
 
 
 def _chk(t, dtype, name):
