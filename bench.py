@@ -295,9 +295,20 @@ def run_ours(args):
         src = "of measured (MEASURED_PEAKS.json)" if peaks else "of fallback (B200_PROFILING.md)"
         if sp_ms >= bp_ms:
             ach = flops / (sp_ms * 1e-3) / 1e12 if sp_ms else 0.0
-            roofline = {"kernel": "spconv_kernel (gather-GEMM, fp32 FFMA this round)", "bound": "tensor", "achieved": ach,
-                        "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak, "traffic": None,
-                        "peak_source": src + ", bf16 dense sustained; the kernel computes in fp32 on CUDA cores",
+            impl = ops.SPCONV_IMPL
+            kname = {"tf32x3": "spconv_tc_kernel<3> (gather -> tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators)",
+                     "tf32": "spconv_tc_kernel<1> (gather -> tcgen05.mma kind::tf32)",
+                     "ffma": "spconv_kernel (gather-GEMM, fp32 FFMA)"}[impl]
+            roofline = {"kernel": kname + "; K=1 linears run on spconv_kernel (fp32 FFMA)", "bound": "tensor", "achieved": ach,
+                        "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak,
+                        "traffic": 41.3e6 if impl != "ffma" else None,
+                        "traffic_note": "dram read+write bytes of one level-2 launch (74->8 ch, 200k rows) from profiles/r01_spconv_tc_v2_ncu_summary.csv",
+                        "peak_source": src + ", bf16 dense sustained (tf32 dense peak is half of it); achieved counts the "
+                                             "algorithmic 2*Cin*Cout*pairs flops once (3xTF32 issues 3 MMAs per product); the kernel is "
+                                             "gather/L2-bound, see memory_view",
+                        "memory_view": {"achieved_GBs": sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms else None, "peak_GBs": hbm_peak,
+                                        "frac": (sp_bytes / (sp_ms * 1e-3) / 1e9 / hbm_peak) if sp_ms else None,
+                                        "bytes": "4(M_in*Cin + M_out*Cout) + 4*K*Cin*Cout + 4*pairs per launch (lower bound: every input row read once)"},
                         "launches_per_step": per_step, "algorithmic_flops_per_step": flops,
                         "algorithmic_bytes_per_step": sp_bytes, "avg_launch_us": 1e3 * sp_ms / max(per_step, 1)}
         else:

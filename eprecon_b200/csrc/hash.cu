@@ -98,12 +98,13 @@ __global__ void kmap_kernel(const int4* __restrict__ out_coords, int m, int batc
   nbr[t] = r;
 }
 
-// inverse of a k==s strided map: for fine row i, the unique (coarse j, offset k) that reaches it
-__global__ void kmap_inverse_kernel(const int* __restrict__ nbr, int m_out, int K, int* __restrict__ inv) {
+// inverse of a k==s strided map as a one-hot neighbour table: up[i, k] = j for the unique (coarse j, offset k) that
+// reaches fine row i (table pre-filled with -1) -- the transposed conv then runs as a plain gather-GEMM
+__global__ void kmap_inverse_kernel(const int* __restrict__ nbr, int m_out, int K, int* __restrict__ up) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)m_out * K) return;
   int i = nbr[t];
-  if (i >= 0) inv[i] = (int)t;  // = j*K + k
+  if (i >= 0) up[(size_t)i * K + (int)(t % K)] = (int)(t / K);
 }
 
 // torchsparse spdownsample for k == s (nn/functional/downsample.py): trunc(c / (s*ts)) * (s*ts), then a
@@ -247,7 +248,7 @@ int ep_kmap_build(const int32_t* out_coords, int64_t m_out, int batch_first, con
   return EP_OK;
 }
 
-// inv must be pre-filled with -1 by the caller (m_in entries)
+// up (int32 [m_in, K]) must be pre-filled with -1 by the caller
 int ep_kmap_inverse(const int32_t* nbr, int64_t m_out, int K, int32_t* inv, cudaStream_t stream) {
   if (m_out <= 0) return EP_ERR_ARG;
   long long total = (long long)m_out * K;

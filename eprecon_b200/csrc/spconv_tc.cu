@@ -102,9 +102,11 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
                  const float* __restrict__ w_hi, const float* __restrict__ w_lo, int nq /*ceil(cin/4)*/,
                  int npad /*total padded cout*/, int nt /*columns of this launch's tile*/, int tmem_cols, int cout,
                  const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m_out,
-                 float* __restrict__ bn_partial, int bn_rows) {
+                 float* __restrict__ bn_partial, int bn_rows, int splits, float* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int NACC = PREC == 3 ? 4 : 1;
+  // split-K over the kernel offsets: blockIdx.z owns offsets [kb, ke) and (when splits > 1) writes raw partial sums
+  const int kb = (int)(((long long)blockIdx.z * K) / splits), ke = (int)(((long long)(blockIdx.z + 1) * K) / splits);
   const int a_bytes = (KCT / 4) * TMR * 16;
   const int b_bytes = (KCT / 4) * nt * 16;
   const int stage_bytes = (PREC == 3 ? 2 : 1) * (a_bytes + b_bytes);
@@ -144,7 +146,7 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
   // kernel offsets with at least one neighbour in the tile
   if (warp == 0) {
     int nk = 0;
-    for (int k = 0; k < K; ++k) {
+    for (int k = kb; k < ke; ++k) {
       int any = 0;
       for (int r = lane; r < TMR; r += 32) any |= (s_nbr[k * TMR + r] >= 0);
       if (__any_sync(0xffffffffu, any)) { if (lane == 0) s_klist[nk] = k; ++nk; }
@@ -280,6 +282,14 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
           for (int i = 0; i < 16; ++i) v[i] += t16[i];
         }
       }
+      if (splits > 1) {  // raw partial sums; bias / statistics are applied by splitk_reduce_kernel
+        if (row < m_out) {
+          float4* dst = reinterpret_cast<float4*>(partial + ((size_t)blockIdx.z * m_out + row) * npad + col0 + cb);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        continue;
+      }
       float s[16], sq[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -308,7 +318,7 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (bn_partial && tid < nt) {
+  if (bn_partial && splits == 1 && tid < nt) {
     const int col = col0 + tid;
     if (col < cout) {
       const float s = (s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]);
@@ -328,6 +338,43 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
   }
 }
 
+// out[row, col] = bias + sum_z partial[z][row][col] (fixed z order), plus the per-64-row-tile BN statistics
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, int m_out, int npad, int cout,
+                     const float* __restrict__ bias, float* __restrict__ out, int ld_out, float* __restrict__ bn_partial) {
+  __shared__ float s_s[4][64], s_q[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 columns x 4 row groups of 16 rows
+  const int row0 = blockIdx.x * 64;
+  for (int c0 = 0; c0 < cout; c0 += 64) {
+    const int col = c0 + tx;
+    float s = 0.f, q = 0.f;
+    if (col < cout) {
+      const float bv = bias ? bias[col] : 0.f;
+      for (int r = 0; r < 16; ++r) {
+        const int row = row0 + ty * 16 + r;
+        if (row < m_out) {
+          float v = 0.f;
+          for (int z = 0; z < splits; ++z) v += partial[((size_t)z * m_out + row) * npad + col];
+          v += bv;
+          out[(size_t)row * ld_out + col] = v;
+          s += v;
+          q = fmaf(v, v, q);
+        }
+      }
+    }
+    if (bn_partial) {
+      s_s[ty][tx] = s;
+      s_q[ty][tx] = q;
+      __syncthreads();
+      if (ty == 0 && col < cout) {
+        bn_partial[((size_t)blockIdx.x * 2 + 0) * cout + col] = (s_s[0][tx] + s_s[1][tx]) + (s_s[2][tx] + s_s[3][tx]);
+        bn_partial[((size_t)blockIdx.x * 2 + 1) * cout + col] = (s_q[0][tx] + s_q[1][tx]) + (s_q[2][tx] + s_q[3][tx]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 inline int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -341,9 +388,24 @@ extern "C" {
 // Weights must be pre-arranged as float[K][nq][npad][4] (w[k][q][n][i] = W[k][4q+i][n], zero padded; npad = cout
 // rounded up to a multiple of 16, and of 128 when larger than 128).  w_lo is only read when prec == 3.
 // bn_partial: NULL or float[ep_spconv_num_row_tiles(m_out), 2, cout].
+// split-K factor for small problems: spread the K kernel offsets over up to ~one wave of CTAs
+static int tc_splits(int64_t m_out, int npad, int K) {
+  const int nt = npad > 128 ? 128 : npad;
+  const long long ctas = (long long)ep_div_up(m_out, TMR) * (npad / nt);
+  if (K < 2 || ctas * 2 > EP_NUM_SMS) return 1;
+  long long s = EP_NUM_SMS / ctas;
+  if (s > K) s = K;
+  return s < 2 ? 1 : (int)s;
+}
+
+size_t ep_spconv_tc_workspace_bytes(int64_t m_out, int npad, int K) {
+  const int s = tc_splits(m_out, npad, K);
+  return s > 1 ? (size_t)s * (size_t)m_out * (size_t)npad * sizeof(float) : 0;
+}
+
 int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, int K, const float* w_hi,
                      const float* w_lo, int npad, int cout, const float* bias, float* out, int ld_out, int64_t m_out,
-                     float* bn_partial, int prec, cudaStream_t stream) {
+                     float* bn_partial, int prec, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (m_out <= 0 || cin < 1 || cout < 1 || K < 1 || ld_in % 4 != 0 || npad % 16 != 0 || npad < cout) return EP_ERR_ARG;
   if (!nbr && K != 1) return EP_ERR_ARG;
   if (prec != 1 && prec != 3) return EP_ERR_ARG;
@@ -364,14 +426,20 @@ int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, in
   if (prec == 3) e = cudaFuncSetAttribute(spconv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   else e = cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return EP_ERR_CUDA;
-  dim3 grid(ep_div_up(m_out, TMR), npad / nt);
+  const int splits = tc_splits(m_out, npad, K);
+  if (splits > 1 && workspace_bytes < ep_spconv_tc_workspace_bytes(m_out, npad, K)) return EP_ERR_WORKSPACE;
+  float* partial = splits > 1 ? (float*)workspace : nullptr;
+  dim3 grid(ep_div_up(m_out, TMR), npad / nt, splits);
   const int bn_rows = ep_div_up(m_out, 64);
   if (prec == 3)
     spconv_tc_kernel<3><<<grid, TC_THREADS + 32, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, (cin + 3) / 4, npad, nt,
-                                                           tmem_cols, cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows);
+                                                           tmem_cols, cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial);
   else
     spconv_tc_kernel<1><<<grid, TC_THREADS + 32, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, (cin + 3) / 4, npad, nt,
-                                                           tmem_cols, cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows);
+                                                           tmem_cols, cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial);
+  if (splits > 1)
+    splitk_reduce_kernel<<<ep_div_up(m_out, 64), 256, 0, stream>>>(partial, splits, (int)m_out, npad, cout, bias, out, ld_out,
+                                                                  bn_partial);
   EP_CHECK_LAUNCH();
   return EP_OK;
 }

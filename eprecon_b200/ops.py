@@ -306,9 +306,11 @@ def spconv(x, cin, nbr, W, cout, bias=None, m_out=None, want_stats=False, out=No
     else:
         prec = 3 if SPCONV_IMPL == "tf32x3" else 1
         w_hi, w_lo, npad = _umma_weights(W, cout, prec)
+        wsb = L.ep_spconv_tc_workspace_bytes(m_out, npad, K)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
         _lib.check(L.ep_spconv_tc_fwd(x.data_ptr(), x.stride(0), cin, _ptr(nbr), K, w_hi.data_ptr(), _ptr(w_lo), npad,
                                       cout, _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
-                                      prec, stream_ptr()), "ep_spconv_tc_fwd")
+                                      prec, _ptr(ws), wsb, stream_ptr()), "ep_spconv_tc_fwd")
     _prof_end(_e)
     return out, part
 

@@ -52,15 +52,9 @@ class VoxelSet:
             coarse = VoxelSet(cc, step)
             offs = ops.kernel_offsets("k2", self.stride, dev)
             nbr_down = ops.kmap_build(cc, False, offs, self.table)           # [Mc,8] -> fine rows
-            inv = torch.full((self.m,), -1, dtype=torch.int32, device=dev)
-            _lib.check(L.ep_kmap_inverse(nbr_down.data_ptr(), mc, 8, inv.data_ptr(), stream_ptr()), "ep_kmap_inverse")
-            # expand inverse (j*8+k) into an [M,8] one-hot neighbour table: the same gather-GEMM kernel runs it
+            # one-hot inverse [M,8] (at most one valid entry per fine row): the same gather-GEMM kernel runs the transposed conv
             nbr_up = torch.full((self.m, 8), -1, dtype=torch.int32, device=dev)
-            hit = inv >= 0
-            rows = torch.nonzero(hit).squeeze(1)
-            if rows.numel():
-                iv = inv[rows].long()
-                nbr_up[rows, iv % 8] = (iv // 8).int()
+            _lib.check(L.ep_kmap_inverse(nbr_down.data_ptr(), mc, 8, nbr_up.data_ptr(), stream_ptr()), "ep_kmap_inverse")
             self._down = (coarse, nbr_down, nbr_up)
         return self._down
 
