@@ -341,6 +341,168 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-pass back-projection: projection + visibility + view count + stable compaction (decoupled
+// look-back over tiles) + bilinear gather in ONE kernel.  Sample positions computed in the visibility
+// phase stay in shared memory for the gather, nothing is recomputed and no intermediate touches HBM.
+// ---------------------------------------------------------------------------------------------
+constexpr int FT = 256;  // threads per CTA
+constexpr int TV = 64;   // candidate voxels per CTA: 4 threads share a voxel's views in the projection phase, and the
+                         // gather phase still has 8 warps for <= 64 survivors (latency hiding needs warps, not voxels)
+constexpr unsigned long long TS_AGG = 1ULL << 32, TS_PREFIX = 2ULL << 32;
+
+template <int C, int MODE>
+__global__ void __launch_bounds__(FT)
+bp_fused_kernel(const int4* __restrict__ coords, int n, const float* __restrict__ origin, float vs,
+                const float* __restrict__ kr, int V, int bs, int H, int W, const float* __restrict__ feats,
+                int min_views, float* __restrict__ count, int4* __restrict__ out_coords,
+                uint32_t* __restrict__ out_vis, int* __restrict__ out_src, float* __restrict__ out, int ldo,
+                float* __restrict__ zbar, unsigned long long* __restrict__ tile_state, int* __restrict__ ticket,
+                int* __restrict__ totals /*[bs+1]*/, int ntiles) {
+  constexpr int G = C / 4, VPW = 32 / G;
+  extern __shared__ float s_dyn[];           // [V*bs*16] KRt | float2 s_pos[V][TV] | float s_z[V][TV]
+  float* s_kr = s_dyn;
+  float2* s_pos = reinterpret_cast<float2*>(s_dyn + ((V * bs * 16 + 3) & ~3));
+  float* s_z = reinterpret_cast<float*>(s_pos + V * TV);
+  __shared__ uint32_t s_mask[TV];
+  __shared__ int4 s_coord[TV];
+  __shared__ int s_list[TV];
+  __shared__ int s_scan[33];
+  __shared__ int s_tile, s_base;
+  const int t = threadIdx.x;
+  if (t == 0) s_tile = atomicAdd(ticket, 1);   // tiles are numbered in scheduling order -> look-back always progresses
+  for (int i = t; i < V * bs * 16; i += FT) s_kr[i] = kr[i];
+  if (t < TV) s_mask[t] = 0;
+  __syncthreads();
+  const int tile = s_tile;
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  // ---- phase A: thread (vox = t % TV, part = t / TV) projects views part, part+4, ... of its voxel
+  {
+    const int vox = t & (TV - 1), part = t / TV;
+    const int i = tile * TV + vox;
+    if (i < n) {
+      const int4 c = coords[i];
+      if (part == 0) s_coord[vox] = c;
+      float wx, wy, wz;
+      world_point(c.y, c.z, c.w, vs, origin + 3 * c.x, wx, wy, wz);
+      uint32_t m = 0;
+      for (int v = part; v < V; v += FT / TV) {
+        ProjOut p = project_one(s_kr + (v * bs + c.x) * 16, wx, wy, wz, wm1, hm1);
+        if (p.vis) {
+          m |= 1u << v;
+          s_pos[v * TV + vox] = make_float2(__fmul_rn(__fdiv_rn(__fadd_rn(p.gx, 1.f), 2.f), wm1),
+                                            __fmul_rn(__fdiv_rn(__fadd_rn(p.gy, 1.f), 2.f), hm1));
+          if (zbar) s_z[v * TV + vox] = p.z;
+        }
+      }
+      if (m) atomicOr(&s_mask[vox], m);
+    }
+  }
+  __syncthreads();
+  // ---- phase B: stable compaction offset (block scan + warp-parallel decoupled look-back)
+  int keep = 0;
+  uint32_t m = 0;
+  int4 c = make_int4(0, 0, 0, 0);
+  const int i = tile * TV + t;
+  if (t < TV && i < n) {
+    m = s_mask[t];
+    c = s_coord[t];
+    const int cnt = __popc(m);
+    count[i] = (float)cnt;
+    keep = cnt >= min_views;
+  }
+  int total;
+  const int rank = ep_block_excl_scan(keep, s_scan, &total);
+  if (t < 32) {
+    volatile unsigned long long* ts = tile_state;
+    if (t == 0) {
+      __threadfence();
+      ts[tile] = (tile == 0 ? TS_PREFIX : TS_AGG) | (unsigned long long)(unsigned)total;
+    }
+    int prefix = 0;
+    int p = tile - 1 - t;
+    bool done = tile == 0;
+    while (!done) {
+      unsigned long long st = TS_PREFIX;            // tiles before 0: an empty prefix
+      if (p >= 0) { do { st = ts[p]; } while ((st >> 32) == 0); }
+      const unsigned has_prefix = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+      const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;
+      int contrib = (t <= first) ? (int)(st & 0xffffffffULL) : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+      prefix += contrib;
+      done = has_prefix != 0;
+      p -= 32;
+    }
+    if (t == 0) {
+      if (tile > 0) { __threadfence(); ts[tile] = TS_PREFIX | (unsigned long long)(unsigned)(prefix + total); }
+      s_base = prefix;
+      if (tile == ntiles - 1) totals[bs] = prefix + total;
+      if (bs == 1 && total) atomicAdd(totals, total);
+    }
+  }
+  if (bs > 1 && keep) atomicAdd(totals + c.x, 1);
+  if (keep) s_list[rank] = t;
+  __syncthreads();
+  const int base = s_base;
+  if (keep) {
+    out_coords[base + rank] = c;
+    out_vis[base + rank] = m;
+    if (out_src) out_src[base + rank] = i;
+  }
+  // ---- phase C: gather (lanes split the channel quads of VPW voxels per warp pass)
+  const int lane = t & 31, warp = t >> 5;
+  const int sub = lane / G, cq = lane % G;
+  const size_t plane = (size_t)H * W * C;
+  const int ngroups = (total + VPW - 1) / VPW;
+  for (int g = warp; g < ngroups; g += FT / 32) {
+    const int k = g * VPW + sub;
+    if (sub < VPW && k < total) {
+      const int tv = s_list[k];
+      const uint32_t msk = s_mask[tv];
+      const int b = bs == 1 ? 0 : s_coord[tv].x;
+      const float cntf = (float)max(__popc(msk), 1);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float zsum = 0.f;
+      uint32_t rem = msk;
+      while (rem) {                         // two visible views per trip: 8 independent 16-byte taps in flight
+        const int v0 = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const int v1 = rem ? __ffs(rem) - 1 : -1;
+        if (v1 >= 0) rem &= rem - 1;
+        const float2 g0 = s_pos[v0 * TV + tv];
+        const float2 g1 = v1 >= 0 ? s_pos[v1 * TV + tv] : g0;
+        float4 s0 = sample_quad(feats + (size_t)(v0 * bs + b) * plane, H, W, C, cq, g0.x, g0.y);
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v1 >= 0) s1 = sample_quad(feats + (size_t)(v1 * bs + b) * plane, H, W, C, cq, g1.x, g1.y);
+        acc.x += s0.x; acc.y += s0.y; acc.z += s0.z; acc.w += s0.w;
+        acc.x += s1.x; acc.y += s1.y; acc.z += s1.z; acc.w += s1.w;
+        if (zbar) { zsum += s_z[v0 * TV + tv]; if (v1 >= 0) zsum += s_z[v1 * TV + tv]; }
+      }
+      float4 mean = make_float4(__fdiv_rn(acc.x, cntf), __fdiv_rn(acc.y, cntf), __fdiv_rn(acc.z, cntf),
+                                __fdiv_rn(acc.w, cntf));
+      float4 res = mean;
+      if (MODE == 1) {
+        float4 var = make_float4(0.f, 0.f, 0.f, 0.f);
+        rem = msk;
+        while (rem) {
+          const int v0 = __ffs(rem) - 1;
+          rem &= rem - 1;
+          const float2 g0 = s_pos[v0 * TV + tv];
+          float4 s0 = sample_quad(feats + (size_t)(v0 * bs + b) * plane, H, W, C, cq, g0.x, g0.y);
+          float dx = s0.x - mean.x, dy = s0.y - mean.y, dz = s0.z - mean.z, dw = s0.w - mean.w;
+          var.x = fmaf(dx, dx, var.x); var.y = fmaf(dy, dy, var.y);
+          var.z = fmaf(dz, dz, var.z); var.w = fmaf(dw, dw, var.w);
+        }
+        res = make_float4(__fdiv_rn(var.x, cntf), __fdiv_rn(var.y, cntf), __fdiv_rn(var.z, cntf),
+                          __fdiv_rn(var.w, cntf));
+      }
+      *reinterpret_cast<float4*>(out + (size_t)(base + k) * ldo + cq * 4) = res;
+      if (zbar && cq == 0) zbar[base + k] = __fdiv_rn(zsum, cntf);
+    }
+  }
+}
+
 template <int MODE>
 int launch_gather(const int4* oc, const uint32_t* ov, int m, const float* feats, int C, int V, int bs, int H, int W,
                   const float* origin, float vs, const float* kr, float* out, int ldo, float* zbar,
@@ -418,6 +580,61 @@ int ep_backproject_gather(const int32_t* out_coords, const uint32_t* out_vis, in
     return launch_gather<1>((const int4*)out_coords, out_vis, (int)m, feats_nhwc, channels, n_views, bs, feat_h,
                             feat_w, origin, voxel_size, krcam, out, ld_out, zbar, stream);
   return EP_ERR_ARG;
+}
+
+size_t ep_backproject_fused_workspace_bytes(int64_t n) {
+  return (size_t)ep_div_up(n > 0 ? n : 1, TV) * sizeof(unsigned long long) + 256;
+}
+
+// One launch: count[n], compacted out_coords / out_vis / out_src / out rows (capacity n each) and totals[bs+1]
+// (survivors per batch entry, grand total).  channels must be one of 24 / 32 / 40 / 80 (the path's pyramids + the
+// fused init map); other widths use the three-pass entry points above.
+int ep_backproject_fused(const int32_t* coords, int64_t n, const float* origin, float voxel_size, const float* krcam,
+                         int n_views, int bs, int feat_h, int feat_w, const float* feats_nhwc, int channels,
+                         int min_views, int mode, float* count, int32_t* out_coords, uint32_t* out_vis,
+                         int32_t* out_src, float* out, int ld_out, float* zbar, int32_t* totals, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream) {
+  if (n <= 0 || n_views < 1 || n_views > kMaxViews || bs < 1 || n > 0x7fffffffLL || ld_out % 4 != 0) return EP_ERR_ARG;
+  if (mode != 0 && mode != 1) return EP_ERR_ARG;
+  if (workspace_bytes < ep_backproject_fused_workspace_bytes(n)) return EP_ERR_WORKSPACE;
+  const int ntiles = ep_div_up(n, TV);
+  unsigned long long* tile_state = (unsigned long long*)workspace;
+  int* ticket = (int*)(tile_state + ntiles);
+  cudaMemsetAsync(workspace, 0, (size_t)ntiles * sizeof(unsigned long long) + sizeof(int), stream);
+  cudaMemsetAsync(totals, 0, sizeof(int) * (bs + 1), stream);
+  const size_t smem = (size_t)(((n_views * bs * 16 + 3) & ~3) + n_views * TV * 2 + n_views * TV) * sizeof(float);
+  if (smem > 160 * 1024) return EP_ERR_UNSUPPORTED;
+#define EP_BP_FUSED(CC, MM)                                                                                           \
+  do {                                                                                                                \
+    if (smem > 48 * 1024 &&                                                                                           \
+        cudaFuncSetAttribute(bp_fused_kernel<CC, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=      \
+            cudaSuccess)                                                                                              \
+      return EP_ERR_CUDA;                                                                                             \
+    bp_fused_kernel<CC, MM><<<ntiles, FT, smem, stream>>>((const int4*)coords, (int)n, origin, voxel_size, krcam,     \
+                                                          n_views, bs, feat_h, feat_w, feats_nhwc, min_views, count,  \
+                                                          (int4*)out_coords, out_vis, out_src, out, ld_out, zbar,     \
+                                                          tile_state, ticket, totals, ntiles);                        \
+  } while (0)
+  if (mode == 0) {
+    switch (channels) {
+      case 24: EP_BP_FUSED(24, 0); break;
+      case 32: EP_BP_FUSED(32, 0); break;
+      case 40: EP_BP_FUSED(40, 0); break;
+      case 80: EP_BP_FUSED(80, 0); break;
+      default: return EP_ERR_UNSUPPORTED;
+    }
+  } else {
+    switch (channels) {
+      case 24: EP_BP_FUSED(24, 1); break;
+      case 32: EP_BP_FUSED(32, 1); break;
+      case 40: EP_BP_FUSED(40, 1); break;
+      case 80: EP_BP_FUSED(80, 1); break;
+      default: return EP_ERR_UNSUPPORTED;
+    }
+  }
+#undef EP_BP_FUSED
+  EP_CHECK_LAUNCH();
+  return EP_OK;
 }
 
 int ep_backproject_grid(const int32_t* out_coords, const uint32_t* out_vis, int64_t m, int n_views, int bs,

@@ -20,7 +20,7 @@ namespace {
 
 constexpr int TMR = 128;      // output rows per CTA (UMMA M)
 constexpr int KCT = 16;       // input channels per stage (2 MMAs of K = 8)
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 3;
 constexpr int TC_THREADS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,7 +97,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // truncation, so the error grows with the number of MMAs chained on one accumulator: keeping the (tiny) cross terms
 // off the main chain and splitting it three ways brings the result back to fp32-FMA grade.
 template <int PREC>
-__global__ void __launch_bounds__(TC_THREADS + 32)
+__global__ void __launch_bounds__(TC_THREADS + 32, 3)
 spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*/, const int* __restrict__ nbr, int K,
                  const float* __restrict__ w_hi, const float* __restrict__ w_lo, int nq /*ceil(cin/4)*/,
                  int npad /*total padded cout*/, int nt /*columns of this launch's tile*/, int tmem_cols, int cout,

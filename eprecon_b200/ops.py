@@ -93,9 +93,37 @@ def backproject(coords, origin, voxel_size, feats_nhwc, krcam, min_views, mode="
     n = coords.shape[0]
     dev = coords.device
     st = stream_ptr()
+    mode_i = {"mean": 0, "meanvar": 1}[mode]
     count = torch.empty(n, dtype=torch.float32, device=dev)
-    vis = torch.empty(n, dtype=torch.int32, device=dev)
     counters = torch.empty(bs + 1, dtype=torch.int32, device=dev)
+    if BP_IMPL == "fused" and C in (24, 32, 40, 80) and out is None:
+        # single pass: outputs are allocated at capacity n and sliced to the survivor count afterwards
+        width = alloc_width or C
+        buf = torch.empty((n, width), dtype=torch.float32, device=dev)
+        out_coords = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        out_vis = torch.empty(n, dtype=torch.int32, device=dev)
+        src = torch.empty(n, dtype=torch.int32, device=dev) if want_src else None
+        zbar = torch.empty(n, dtype=torch.float32, device=dev) if want_zbar else None
+        wsb = L.ep_backproject_fused_workspace_bytes(n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        _prof_work("bp_gather", lambda: {"bytes": 0, "n_in": n, "C": C, "deferred": True})
+        _e = _prof_begin("bp_gather")
+        _lib.check(L.ep_backproject_fused(coords.data_ptr(), n, origin.data_ptr(), float(voxel_size), krcam.data_ptr(), V, bs,
+                                          H, W, feats_nhwc.data_ptr(), C, int(min_views), mode_i, count.data_ptr(),
+                                          out_coords.data_ptr(), out_vis.data_ptr(), _ptr(src), buf.data_ptr(), width,
+                                          _ptr(zbar), counters.data_ptr(), ws.data_ptr(), wsb, st), "ep_backproject_fused")
+        _prof_end(_e)
+        host = counters.tolist()   # the one host sync of this op (output size is data dependent)
+        m = host[bs]
+        if PROFILE is not None and PROFILE.get("mode") == "work":
+            PROFILE["bp_gather_work"][-1] = {"bytes": 4 * V * C * H * W + 64 * V + 20 * n + (16 + 4 * C) * m, "n_in": n,
+                                             "n_out": m, "C": C}
+        if any(v < min_valid for v in host[:bs]):
+            return None
+        return {"feat": buf[:m, :C], "coords": out_coords[:m], "count": count, "vis": out_vis[:m],
+                "src": src[:m] if src is not None else None, "zbar": zbar[:m] if zbar is not None else None,
+                "n_valid": host[:bs], "buffer": buf[:m]}
+    vis = torch.empty(n, dtype=torch.int32, device=dev)
     ws_bytes = L.ep_backproject_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     _lib.check(L.ep_backproject_count(coords.data_ptr(), n, origin.data_ptr(), float(voxel_size), krcam.data_ptr(),
@@ -124,9 +152,8 @@ def backproject(coords, origin, voxel_size, feats_nhwc, krcam, min_views, mode="
                                      "n_out": m, "C": C})
     _e = _prof_begin("bp_gather")
     _lib.check(L.ep_backproject_gather(out_coords.data_ptr(), out_vis.data_ptr(), m, feats_nhwc.data_ptr(), C, V, bs,
-                                       H, W, origin.data_ptr(), float(voxel_size), krcam.data_ptr(),
-                                       {"mean": 0, "meanvar": 1}[mode], out.data_ptr() + 4 * out_col, out.shape[1],
-                                       _ptr(zbar), st), "ep_backproject_gather")
+                                       H, W, origin.data_ptr(), float(voxel_size), krcam.data_ptr(), mode_i,
+                                       out.data_ptr() + 4 * out_col, out.shape[1], _ptr(zbar), st), "ep_backproject_gather")
     _prof_end(_e)
     return {"feat": out[:, out_col:out_col + C], "coords": out_coords, "count": count, "vis": out_vis, "src": src,
             "zbar": zbar, "n_valid": host[:bs], "buffer": out}
@@ -251,6 +278,9 @@ def kmap_build(out_coords, batch_first, offsets, table, shape=None):
 # =====================================================================================================
 # dense-per-row math
 # =====================================================================================================
+# back-projection: "fused" = single-pass kernel (count + look-back compaction + gather), "3pass" = count / compact / gather
+BP_IMPL = os.environ.get("EPRECON_BP", "fused")
+
 # "ffma" = fp32 CUDA-core gather-GEMM (csrc/spconv.cu); "tf32x3" / "tf32" = tcgen05 tensor-core kernel (csrc/spconv_tc.cu)
 SPCONV_IMPL = os.environ.get("EPRECON_SPCONV", "tf32x3")
 _UMMA_CACHE = {}

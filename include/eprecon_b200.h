@@ -48,6 +48,14 @@ int ep_backproject_gather(const int32_t* out_coords, const uint32_t* out_vis, in
                           int channels, int n_views, int bs, int feat_h, int feat_w, const float* origin,
                           float voxel_size, const float* krcam, int mode, float* out, int ld_out, float* zbar,
                           cudaStream_t stream);
+/* single-pass variant (count + stable compaction by decoupled look-back + gather in one kernel); outputs have capacity n,
+ * totals[bs+1] = survivors per batch entry and the grand total.  channels in {24,32,40,80}. */
+size_t ep_backproject_fused_workspace_bytes(int64_t n);
+int ep_backproject_fused(const int32_t* coords, int64_t n, const float* origin, float voxel_size, const float* krcam,
+                         int n_views, int bs, int feat_h, int feat_w, const float* feats_nhwc, int channels,
+                         int min_views, int mode, float* count, int32_t* out_coords, uint32_t* out_vis,
+                         int32_t* out_src, float* out, int ld_out, float* zbar, int32_t* totals, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream);
 int ep_backproject_grid(const int32_t* out_coords, const uint32_t* out_vis, int64_t m, int n_views, int bs,
                         int feat_h, int feat_w, const float* origin, float voxel_size, const float* krcam,
                         float* im_grid, uint8_t* mask, cudaStream_t stream);

@@ -51,7 +51,9 @@ def main(iters=20):
         coords = coords.to(dev)
         V, bs, C, H, W = feats.shape
         nhwc = ops.to_nhwc(feats)
+        ops.BP_IMPL = "3pass"
         res = ops.backproject(coords, origin, 0.04, nhwc, kr, minv, want_src=True)
+        ops.BP_IMPL = "fused"
         n, m = coords.shape[0], res["coords"].shape[0]
         out = torch.empty((m, C), device=dev)
         count = torch.empty(n, device=dev)
@@ -83,12 +85,33 @@ def main(iters=20):
             if it >= 3:
                 for k in range(4):
                     t[k] += ev[k].elapsed_time(ev[k + 1]) / iters
+        # fused single-pass kernel (same outputs, one launch)
+        bufF = torch.empty((n, C), device=dev)
+        ocF = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        ovF = torch.empty(n, dtype=torch.int32, device=dev)
+        totF = torch.empty(2, dtype=torch.int32, device=dev)
+        wsf = L.ep_backproject_fused_workspace_bytes(n)
+        wsF = torch.empty(wsf, dtype=torch.uint8, device=dev)
+        tf = 0.0
+        ef = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for it in range(iters + 3):
+            flush.zero_()
+            ef[0].record()
+            L.ep_backproject_fused(coords.data_ptr(), n, origin.data_ptr(), 0.04, kr.data_ptr(), V, bs, H, W, nhwc.data_ptr(), C,
+                                   minv, 0, count.data_ptr(), ocF.data_ptr(), ovF.data_ptr(), 0, bufF.data_ptr(), C, 0,
+                                   totF.data_ptr(), wsF.data_ptr(), wsf, st)
+            ef[1].record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                tf += ef[0].elapsed_time(ef[1]) / iters
+        assert int(totF[1].item()) == m and torch.equal(ocF[:m], oc) and torch.allclose(bufF[:m], out, rtol=1e-5, atol=1e-6)
         visible = float(res["count"].sum().item()) / max(n, 1)
         bytes_alg = 4 * V * C * H * W + 64 * V + 20 * n + (16 + 4 * C) * m
         tot = t[1] + t[2] + t[3]
         print(json.dumps({"level": level, "n_in": n, "n_out": m, "C": C, "HW": [H, W], "mean_visible_views": round(visible, 2),
                           "ms_transpose": round(t[0], 4), "ms_count": round(t[1], 4), "ms_compact": round(t[2], 4),
-                          "ms_gather": round(t[3], 4), "alg_MB": round(bytes_alg / 1e6, 2),
+                          "ms_gather": round(t[3], 4), "ms_fused_single_pass": round(tf, 4),
+                          "GBs_fused": round(bytes_alg / tf / 1e6, 1), "frac_fused": round(bytes_alg / tf / 1e6 / peak, 3), "alg_MB": round(bytes_alg / 1e6, 2),
                           "GBs_all3": round(bytes_alg / tot / 1e6, 1), "frac_all3": round(bytes_alg / tot / 1e6 / peak, 3),
                           "GBs_gather_only": round((4 * V * C * H * W + (20 + 4 * C) * m) / t[3] / 1e6, 1)}))
 
