@@ -179,12 +179,13 @@ int ep_affine_act(const float* a, int ld_a, const float* ss_a, const float* b, i
 int ep_layernorm(const float* x, int ld_x, const float* res, int ld_res, int relu_before, const float* gamma,
                  const float* beta, float eps, int relu_after, int64_t m, int c, float* out, int ld_out,
                  cudaStream_t stream) {
-  if (m <= 0 || c < 1 || c > 512) return EP_ERR_ARG;
+  if (m <= 0 || c < 1 || c > 1024) return EP_ERR_ARG;
   const int blocks = ep_div_up(m * 32, 256);
   if (c <= 32) layernorm_kernel<1><<<blocks, 256, 0, stream>>>(x, ld_x, res, ld_res, relu_before, gamma, beta, eps, relu_after, (int)m, c, out, ld_out);
   else if (c <= 64) layernorm_kernel<2><<<blocks, 256, 0, stream>>>(x, ld_x, res, ld_res, relu_before, gamma, beta, eps, relu_after, (int)m, c, out, ld_out);
   else if (c <= 128) layernorm_kernel<4><<<blocks, 256, 0, stream>>>(x, ld_x, res, ld_res, relu_before, gamma, beta, eps, relu_after, (int)m, c, out, ld_out);
-  else layernorm_kernel<16><<<blocks, 256, 0, stream>>>(x, ld_x, res, ld_res, relu_before, gamma, beta, eps, relu_after, (int)m, c, out, ld_out);
+  else if (c <= 512) layernorm_kernel<16><<<blocks, 256, 0, stream>>>(x, ld_x, res, ld_res, relu_before, gamma, beta, eps, relu_after, (int)m, c, out, ld_out);
+  else layernorm_kernel<32><<<blocks, 256, 0, stream>>>(x, ld_x, res, ld_res, relu_before, gamma, beta, eps, relu_after, (int)m, c, out, ld_out);
   EP_CHECK_LAUNCH();
   return EP_OK;
 }

@@ -97,3 +97,45 @@ int ep_union_sites(const int32_t* sites, int64_t u, int dy, int dz, int batch, i
 }
 
 }  // extern "C"
+
+// ---- panoptic level alignment (models/neucon_network.py:516-544): keep a coarse voxel only if a finer-level voxel
+// survives inside it.  The reference does this with an O(N*M) broadcast compare of coordinate rows; here the finer set
+// marks its parents in a byte volume and the coarse set looks itself up.
+namespace {
+__global__ void mark_parents_kernel(const int4* __restrict__ coords, int n, int step, int dx, int dy, int dz, int bs,
+                                    uint8_t* __restrict__ vol) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 c = coords[i];  // (b, x, y, z) in finest-voxel units; parent cell index = floor(coord / step)
+  int x = c.y / step, y = c.z / step, z = c.w / step;
+  if (c.x >= 0 && c.x < bs && x >= 0 && x < dx && y >= 0 && y < dy && z >= 0 && z < dz)
+    vol[(((size_t)c.x * dx + x) * dy + y) * dz + z] = 1;
+}
+__global__ void lookup_marks_kernel(const int4* __restrict__ coords, int n, int step, int dx, int dy, int dz, int bs,
+                                    const uint8_t* __restrict__ vol, uint8_t* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 c = coords[i];
+  int x = c.y / step, y = c.z / step, z = c.w / step;
+  bool in = c.x >= 0 && c.x < bs && x >= 0 && x < dx && y >= 0 && y < dy && z >= 0 && z < dz;
+  flags[i] = in ? vol[(((size_t)c.x * dx + x) * dy + y) * dz + z] : 0;
+}
+}  // namespace
+
+extern "C" {
+// vol: uint8 [bs, dx, dy, dz], pre-zeroed.  coords are non-negative (fragment-local) voxel indices.
+int ep_mark_parents(const int32_t* coords, int64_t n, int step, int dx, int dy, int dz, int bs, uint8_t* vol,
+                    cudaStream_t stream) {
+  if (n <= 0 || step < 1) return EP_ERR_ARG;
+  mark_parents_kernel<<<ep_div_up(n, 256), 256, 0, stream>>>((const int4*)coords, (int)n, step, dx, dy, dz, bs, vol);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+int ep_lookup_marks(const int32_t* coords, int64_t n, int step, int dx, int dy, int dz, int bs, const uint8_t* vol,
+                    uint8_t* flags, cudaStream_t stream) {
+  if (n <= 0 || step < 1) return EP_ERR_ARG;
+  lookup_marks_kernel<<<ep_div_up(n, 256), 256, 0, stream>>>((const int4*)coords, (int)n, step, dx, dy, dz, bs, vol, flags);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+}  // extern "C"

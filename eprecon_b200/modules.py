@@ -20,7 +20,7 @@ from .tensor import PointTensor  # noqa: F401  (re-exported for callers that bui
 
 __all__ = ["SPVCNN", "SConv3d", "ConvGRU", "SparseSubMConv3d", "Linear4xTrans", "Spares3dELAN", "SubMconv3dBlock",
            "SparseConv3d_Residual", "Fusion_Block", "ELAN", "Conv2d_Block", "Conv2d_Residual_Block",
-           "Linear_Residual", "BasicConvolutionBlock", "BasicDeconvolutionBlock", "ResidualBlock"]
+           "Linear_Residual", "BasicConvolutionBlock", "BasicDeconvolutionBlock", "ResidualBlock", "Panoptic_Feat_Fusion"]
 
 
 # ------------------------------------------------------------------------------------- parameter holders
@@ -457,7 +457,43 @@ class Linear_Residual(nn.Module):
                              eps=self.norm.eps)[:, :self.dim]
 
 
+class Panoptic_Feat_Fusion(nn.Module):
+    """Parameter-compatible mirror of models/modules.py:485-580.  Only `generate_mask_features` is on NeuConNet.forward's
+    path (neucon_network.py:557); the img/occ fusion MLPs are kept so reference checkpoints load by name."""
+
+    def __init__(self, self_channel, panoptic_channel, ch_initialization):
+        super().__init__()
+        self.img2panoptic_0 = nn.Linear(ch_initialization[2], panoptic_channel)
+        self.occ2panoptic_0 = nn.Linear(self_channel, panoptic_channel)
+        self.pre_fusion = nn.Linear(panoptic_channel * 2, panoptic_channel)
+        self.pre_fusion_0 = Linear_Residual(panoptic_channel)
+        self.pre_fusion_1 = Linear_Residual(panoptic_channel)
+        self.mask_feat_extraction_0 = SparseConv3d_Residual(panoptic_channel, 3)
+        self.mask_feat_extraction_1 = SparseConv3d_Residual(panoptic_channel, 3)
+        self.mask_feat_extraction_2 = SparseConv3d_Residual(panoptic_channel, 3)
+
+    @torch.no_grad()
+    def generate_mask_features(self, panoptic_feats, coords_b, coords_xyz, batch_size, spitial_shape):
+        coords = torch.cat([coords_b.unsqueeze(1), coords_xyz], dim=1)
+        sites = SubMSites(coords, spitial_shape)   # one table for the three submanifold convs
+        x = panoptic_feats
+        for blk in (self.mask_feat_extraction_0, self.mask_feat_extraction_1, self.mask_feat_extraction_2):
+            x = blk(x=x, coords=coords, spitial_shape=spitial_shape, bs=batch_size, sites=sites)
+        return x
+
+
 # --------------------------------------------------------------------- dense 2-D blocks (stay on cuDNN, SURVEY a3)
+def _bn2d(x, bn):
+    """Train-mode BatchNorm2d (statistics of the current views, biased variance) as one var_mean reduction + one fused
+    elementwise pass: cuDNN's small-batch training kernel takes ~55 us per call on these 9 x C x 60 x 80 maps, this takes
+    ~15 us, and all of it sits inside the captured CUDA graph.  Falls back to nn.BatchNorm2d.forward in eval mode."""
+    if not bn.training:
+        return bn(x)
+    var, mean = torch.var_mean(x, dim=(0, 2, 3), unbiased=False, keepdim=True)
+    scale = bn.weight.view(1, -1, 1, 1) * torch.rsqrt(var + bn.eps)
+    return torch.addcmul(bn.bias.view(1, -1, 1, 1) - mean * scale, x, scale)
+
+
 class Conv2d_Block(nn.Module):
     def __init__(self, C_in, C_out, Kernel):
         super().__init__()
@@ -466,7 +502,7 @@ class Conv2d_Block(nn.Module):
         self.act = nn.ReLU()
 
     def forward(self, x):
-        return self.act(self.bn(self.conv(x)))
+        return self.act(_bn2d(self.conv(x), self.bn))
 
 
 class Conv2d_Residual_Block(nn.Module):
@@ -477,7 +513,7 @@ class Conv2d_Residual_Block(nn.Module):
         self.relu = nn.ReLU()
 
     def forward(self, x):
-        return self.bn(self.relu(self.conv(x)) + x)
+        return _bn2d(self.relu(self.conv(x)) + x, self.bn)
 
 
 class ELAN(nn.Module):
@@ -512,6 +548,6 @@ class Fusion_Block(nn.Module):
         self.ELAN = ELAN(C)
 
     def forward(self, x):
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.relu(_bn2d(self.conv1(x), self.bn1))
+        out = self.relu(_bn2d(self.conv2(out), self.bn2))
         return self.ELAN(out)

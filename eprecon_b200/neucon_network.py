@@ -25,7 +25,7 @@ except Exception:  # pragma: no cover
 
 from . import _lib, ops
 from .gru_fusion import GRUFusion
-from .modules import SPVCNN, Linear4xTrans
+from .modules import SPVCNN, Linear4xTrans, Panoptic_Feat_Fusion
 from .occupancy_initialization import Back_Project, Occupancy_Initialization
 from .tensor import PointTensor
 
@@ -59,6 +59,10 @@ class NeuConNet(nn.Module):
         self.occ_preds = nn.ModuleList()
         self.panoptic_preds = nn.ModuleList()
         self.initialization = Occupancy_Initialization(ch_initialization, ch_initialization_down, n_views)
+        self.panoptic_feat_fusion = Panoptic_Feat_Fusion(channels[2], panoptic_channels, ch_initialization)
+        # First stage of the panoptic branch (neucon_network.py:516-560): level alignment, per-level panoptic MLPs and the
+        # submanifold mask features.  Off by default: BASELINE configs[1] is the TSDF path; the decoder itself is not built yet.
+        self.with_panoptic_features = False
         for i in range(len(cfg.THRESHOLDS)):
             self.back_projection.append(Back_Project(ch_initialization[i], materialize_grid=False))
             self.sp_convs.append(SPVCNN(num_classes=1, in_channels=ch_in[i], pres=1, cr=1 / 2 ** i,
@@ -149,6 +153,7 @@ class NeuConNet(nn.Module):
         # --------------------------------------------------------------------- coarse-to-fine loop (:348-511)
         pre_feat = pre_coords = None
         pre_c = 0
+        pano_feats, pano_coords = [], []
         for i in range(cfg.N_LAYER):
             interval = 2 ** (self.n_scales - i)
             scale = self.n_scales - i
@@ -242,10 +247,49 @@ class NeuConNet(nn.Module):
             pre_tsdf = ops.gather_rows(tsdf_c, 1, index=index)
             pre_feat[:, cv] = pre_tsdf[:, 0]
             pre_feat[:, cv + 1] = ops.gather_rows(occ_c, 1, index=index)[:, 0]
+            if self.with_panoptic_features:
+                pano_feats.append(ops.gather_rows(feat_all, cv + c_img, index=index))
+                pano_coords.append(pre_coords)
             self.last_sizes[f"level{i}"] = {"candidates": int(res["count"].shape[0]), "projected": m, "fused": u,
                                             "occupied": num}
             if i == cfg.N_LAYER - 1:
                 outputs["coords"] = pre_coords.long()
                 outputs["tsdf"] = pre_tsdf[:, :1]
         outputs["panoptic_info"] = None
+        if self.with_panoptic_features:
+            outputs["panoptic_features"] = self.panoptic_prepare(pano_coords, pano_feats, bs)
         return outputs, loss_dict
+
+    @torch.no_grad()
+    def panoptic_prepare(self, coords, feats, bs):
+        """models/neucon_network.py:516-560: (1) keep a level-1 / level-0 voxel only if an occupied level-2 voxel lies inside
+        it (the reference's O(N*M) row compare becomes parent marking in a byte volume), (2) per-level Linear4xTrans to 48
+        channels, (3) three residual submanifold convs on the level-2 sites -> mask features."""
+        L = _L()
+        st = ops.stream_ptr()
+        dev = coords[2].device
+        dims = [int(n) for n in self.cfg.N_VOX]
+        out_c, out_f = [None, None, coords[2]], [None, None, feats[2]]
+        for lvl, step in ((1, 2), (0, 4)):
+            d = [n // step for n in dims]
+            vol = torch.zeros(bs * d[0] * d[1] * d[2], dtype=torch.uint8, device=dev)
+            _lib.check(L.ep_mark_parents(coords[2].data_ptr(), coords[2].shape[0], step, d[0], d[1], d[2], bs, vol.data_ptr(), st),
+                       "ep_mark_parents")
+            n = coords[lvl].shape[0]
+            flags = torch.empty(n, dtype=torch.uint8, device=dev)
+            _lib.check(L.ep_lookup_marks(coords[lvl].data_ptr(), n, step, d[0], d[1], d[2], bs, vol.data_ptr(), flags.data_ptr(),
+                                         st), "ep_lookup_marks")
+            index, _ = ops.compact_flags(flags)
+            out_c[lvl] = ops.gather_coords(coords[lvl], index)
+            out_f[lvl] = ops.gather_rows(feats[lvl], feats[lvl].shape[1], index=index)
+        pf = [self.panoptic_preds[p](out_f[p]) for p in range(3)]
+        shape = tuple(dims)
+        mask_chunks = []
+        for b in range(bs):
+            sel = slice(None) if bs == 1 else torch.nonzero(out_c[2][:, 0] == b).squeeze(1)
+            cb = out_c[2][sel]
+            mask_chunks.append(self.panoptic_feat_fusion.generate_mask_features(
+                panoptic_feats=pf[2][sel], coords_b=torch.zeros_like(cb[:, 0]), coords_xyz=cb[:, 1:], batch_size=1,
+                spitial_shape=shape))
+        return {"coords": [c.long() for c in out_c], "feats": pf,
+                "mask_features": mask_chunks[0] if bs == 1 else torch.cat(mask_chunks, 0)}

@@ -154,6 +154,13 @@ int ep_union_flags(const int32_t* vol_a, const int32_t* vol_b, int64_t n, uint8_
 int ep_union_sites(const int32_t* sites, int64_t u, int dy, int dz, int batch, int scale, const int32_t* vol_a,
                    const int32_t* vol_b, int32_t* out_coords, int32_t* row_a, int32_t* row_b, cudaStream_t stream);
 
+
+/* ---- panoptic level alignment (models/neucon_network.py:516-544): hash-free parent marking instead of an O(N*M) compare */
+int ep_mark_parents(const int32_t* coords, int64_t n, int step, int dx, int dy, int dz, int bs, uint8_t* vol,
+                    cudaStream_t stream);
+int ep_lookup_marks(const int32_t* coords, int64_t n, int step, int dx, int dy, int dz, int bs, const uint8_t* vol,
+                    uint8_t* flags, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

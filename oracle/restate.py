@@ -497,3 +497,41 @@ def neucon_forward(sd, cfg, features, features_b, inputs, state, trace=None, tea
             out["level"] = i
             break
     return out
+
+
+# ======================================================================= panoptic feature preparation (next row)
+def _subm_residual(sd, p, x, coords, shape):
+    """SparseConv3d_Residual.forward (models/modules.py:476-482)."""
+    y = F.relu(_subm(sd, p + ".SConv3d.sparsesubmconv3d", x, coords, shape, 3))
+    return _ln(x + y, sd, p + ".norm")
+
+
+def panoptic_prepare(sd, cfg, trace, chunk=2048):
+    """models/neucon_network.py:516-560, bs == 1: level alignment by coordinate-row equality (the reference's broadcast
+    compare, chunked here to bound memory), per-level Linear4xTrans, three residual SubM convs for the mask features."""
+    coords = [trace[f"l{i}"]["coords"][trace[f"l{i}"]["occupancy"]] for i in range(3)]
+    feats = [trace[f"l{i}"]["feat_all"][trace[f"l{i}"]["occupancy"]] for i in range(3)]
+
+    def member(a, b):  # rows of a that occur in b
+        out = torch.zeros(len(a), dtype=torch.bool)
+        for s0 in range(0, len(a), chunk):
+            blk = a[s0:s0 + chunk]
+            hit = torch.zeros(len(blk), dtype=torch.bool)
+            for t0 in range(0, len(b), 8192):
+                hit |= (blk.unsqueeze(1) == b[t0:t0 + 8192].unsqueeze(0)).all(2).any(1)
+            out[s0:s0 + chunk] = hit
+        return out
+
+    down = torch.unique(torch.cat([coords[2][:, :1], torch.floor_divide(coords[2][:, 1:], 2) * 2], 1), dim=0)
+    m1 = member(coords[1], down)
+    down_b = torch.unique(torch.cat([down[:, :1], torch.floor_divide(down[:, 1:], 4) * 4], 1), dim=0)
+    m0 = member(coords[0], down_b)
+    coords[1], feats[1] = coords[1][m1], feats[1][m1]
+    coords[0], feats[0] = coords[0][m0], feats[0][m0]
+    pf = [linear4x(sd, f"panoptic_preds.{p}", feats[p]) for p in range(3)]
+    shape = tuple(int(n) for n in cfg.N_VOX)
+    cz = torch.cat([torch.zeros_like(coords[2][:, :1]), coords[2][:, 1:]], 1).int()
+    x = pf[2]
+    for k in range(3):
+        x = _subm_residual(sd, f"panoptic_feat_fusion.mask_feat_extraction_{k}", x, cz, shape)
+    return {"coords": coords, "feats": pf, "mask_features": x}

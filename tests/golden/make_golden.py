@@ -65,6 +65,9 @@ def main():
         net.sp_convs[i].register_forward_hook(hook(f"spv{i}"))
         net.tsdf_preds[i].register_forward_hook(hook(f"tsdf{i}"))
         net.occ_preds[i].register_forward_hook(occ_hook(i))
+    for p in range(3):
+        net.panoptic_preds[p].register_forward_hook(hook(f"pano{p}"))
+    net.panoptic_feat_fusion.mask_feat_extraction_2.register_forward_hook(hook("mask_feats"))
     inputs, fa, fb = synth.make_fragment(seed=SMALL["seed"], n_views=SMALL["n_views"], image_hw=SMALL["image_hw"],
                                          n_vox=SMALL["n_vox"])
     with torch.no_grad():
@@ -93,6 +96,9 @@ def main():
         put(f"gru{i}_values", rec["gru"][i][1])
         put(f"tsdf{i}", rec[f"tsdf{i}"])
         put(f"occ{i}", rec[f"occ{i}"])
+    for p in range(3):
+        put(f"pano{p}", rec[f"pano{p}"])
+    put("mask_feats", rec["mask_feats"])
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "neucon_small.npz")
     np.savez_compressed(path, **g)
     print("wrote", path, os.path.getsize(path), "bytes; thresholds", cfg.THRESHOLDS,

@@ -127,3 +127,31 @@ def test_second_fragment_fuses_with_global_state(runs):
             assert rel(net.trace[f"l{lvl}"]["feat_all"], ot[f"l{lvl}"]["feat_all"]) < RTOL, (frag, lvl)
         assert torch.equal(out["coords"].cpu(), oout["coords"])
         assert rel(out["tsdf"], oout["tsdf"]) < RTOL
+
+
+def test_panoptic_feature_preparation(runs):
+    """CUDA level alignment (parent marking) + panoptic MLPs + SubM mask features vs the oracle's row-compare version."""
+    from oracle import restate
+    from eprecon_b200.neucon_network import NeuConNet
+    g, oout, ot, out_t, tt, out_f, ft = runs
+    n_vox = tuple(int(v) for v in g["n_vox"])
+    cfg = synth.make_cfg(n_vox=n_vox)
+    cfg.THRESHOLDS = [float(v) for v in g["thresholds"]]
+    net = NeuConNet(cfg)
+    sd = synth.synthetic_state_dict(net, 1)
+    with torch.no_grad():
+        want = restate.panoptic_prepare(sd, cfg, ot)
+    net = net.cuda()
+    net.with_panoptic_features = True
+    inputs, fa, fb = synth.make_fragment(seed=int(g["seed"]), n_views=int(g["n_views"]),
+                                         image_hw=tuple(int(v) for v in g["image_hw"]), n_vox=n_vox)
+    cin = {k: (v.cuda() if torch.is_tensor(v) else ([t.cuda() for t in v] if isinstance(v, list) and torch.is_tensor(v[0]) else v))
+           for k, v in inputs.items()}
+    cin["scene"] = ["scene_pano"]
+    net.trace, net.teacher = None, ot
+    out, _ = net([[t.cuda() for t in f] for f in fa], [[t.cuda() for t in f] for f in fb], cin, {})
+    pf = out["panoptic_features"]
+    for p in range(3):
+        assert torch.equal(pf["coords"][p].cpu(), want["coords"][p])          # aligned voxel sets, bit-exact, same order
+        assert rel(pf["feats"][p], want["feats"][p]) < RTOL
+    assert rel(pf["mask_features"], want["mask_features"]) < RTOL

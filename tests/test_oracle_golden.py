@@ -85,3 +85,22 @@ def test_final_sparse_tsdf_matches_reference(small_run):
     assert np.all(np.diff(im) > 0) and np.all(np.diff(ir) > 0)
     scale = np.abs(g["final_tsdf"]).max()
     assert np.abs(out["tsdf"].numpy()[im] - g["final_tsdf"][ir]).max() <= 2e-4 * scale
+
+
+def test_panoptic_feature_preparation_matches_reference(small_run):
+    """Next-row work (SURVEY 8f #1, first stage): level alignment + per-level panoptic MLPs + SubM mask features."""
+    from oracle import restate
+    from eprecon_b200.neucon_network import NeuConNet
+    g, out, tr = small_run
+    cfg = synth.make_cfg(n_vox=tuple(int(v) for v in g["n_vox"]))
+    sd = synth.synthetic_state_dict(NeuConNet(cfg), 1)
+    with torch.no_grad():
+        pp = restate.panoptic_prepare(sd, cfg, tr)
+    for p in range(3):
+        # the reference's level-2 set differs from the restatement's by the 2 threshold-tie voxels (see the final-TSDF test):
+        # compare shapes with that slack and the sampled rows through their coordinates' order-insensitive statistics
+        want_n = int(g[f"pano{p}_shape"][0])
+        assert abs(pp["feats"][p].shape[0] - want_n) <= 4 and pp["feats"][p].shape[1] == 48
+        assert abs(float(pp["feats"][p].double().abs().sum()) - float(g[f"pano{p}_abssum"])) <= 2e-4 * float(g[f"pano{p}_abssum"])
+    assert abs(pp["mask_features"].shape[0] - int(g["mask_feats_shape"][0])) <= 4
+    assert abs(float(pp["mask_features"].double().abs().sum()) - float(g["mask_feats_abssum"])) <= 2e-4 * float(g["mask_feats_abssum"])
