@@ -22,6 +22,9 @@ constexpr int TMR = 128;      // output rows per CTA (UMMA M)
 constexpr int KCT = 16;       // input channels per stage (2 MMAs of K = 8)
 constexpr int NSTAGE = 3;
 constexpr int TC_THREADS = 256;
+constexpr int NBS = TMR + 1;  // row stride of the staged neighbour table (odd -> conflict-free when lanes run over offsets)
+constexpr int APL = TMR + 2;  // float4 slots per K-chunk plane of the A tile: 128 rows + 32 B pad, so the 4 chunks of a row
+                              // land in different banks (lanes run along a row's channels for coalesced gathers)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -78,10 +81,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float tf32_round(float x) {  // round-to-nearest-even to 10 mantissa bits
-  uint32_t u = __float_as_uint(x);
-  u += 0x00000FFFu + ((u >> 13) & 1u);
-  return __uint_as_float(u & 0xFFFFE000u);
+__device__ __forceinline__ float tf32_round(float x) {  // round-to-nearest to 10 mantissa bits, one instruction
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -107,7 +110,7 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
   constexpr int NACC = PREC == 3 ? 4 : 1;
   // split-K over the kernel offsets: blockIdx.z owns offsets [kb, ke) and (when splits > 1) writes raw partial sums
   const int kb = (int)(((long long)blockIdx.z * K) / splits), ke = (int)(((long long)(blockIdx.z + 1) * K) / splits);
-  const int a_bytes = (KCT / 4) * TMR * 16;
+  const int a_bytes = (KCT / 4) * APL * 16;
   const int b_bytes = (KCT / 4) * nt * 16;
   const int stage_bytes = (PREC == 3 ? 2 : 1) * (a_bytes + b_bytes);
   int* s_nbr = reinterpret_cast<int*>(smem_raw + (size_t)NSTAGE * stage_bytes);  // [K][128] neighbour rows of the tile
@@ -132,36 +135,39 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
     mbar_init(&all_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // the tile's neighbour table, transposed to [k][row] (coalesced global read, conflict-free smem use)
-  for (int e = tid; e < TMR * K; e += blockDim.x) {
-    const int r = e / K, k = e - r * K;
-    const int j = row0 + r;
-    int v = -1;
-    if (j < m_out) v = nbr ? nbr[(size_t)j * K + k] : j;
-    s_nbr[k * TMR + r] = v;
-  }
+  if (tid == 0) s_nk = 0;   // reused as the bit mask of kernel offsets that have a neighbour in this tile
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // kernel offsets with at least one neighbour in the tile
-  if (warp == 0) {
-    int nk = 0;
-    for (int k = kb; k < ke; ++k) {
+  // stage the tile's neighbour table transposed to [k][row]: one warp per row, lanes over the K offsets (coalesced
+  // global read, conflict-free smem write thanks to the odd stride) and collect the active-offset mask on the way
+  {
+    const int nwarps = blockDim.x >> 5;
+    for (int kq = lane; kq < K; kq += 32) {
+      const bool mine = kq >= kb && kq < ke;
       int any = 0;
-      for (int r = lane; r < TMR; r += 32) any |= (s_nbr[k * TMR + r] >= 0);
-      if (__any_sync(0xffffffffu, any)) { if (lane == 0) s_klist[nk] = k; ++nk; }
+      for (int r = warp; r < TMR; r += nwarps) {
+        const int j = row0 + r;
+        int v = -1;
+        if (j < m_out) v = nbr ? nbr[(size_t)j * K + kq] : j;
+        s_nbr[kq * NBS + r] = v;
+        any |= (v >= 0);
+      }
+      if (any && mine) atomicOr(&s_nk, 1 << kq);
     }
-    if (lane == 0) s_nk = nk;
   }
   __syncthreads();
+  const unsigned kmask = (unsigned)s_nk;   // every thread walks the set bits in ascending order: the active offsets
   const uint32_t tmem_d = tmem_base_s;
-  const int nk = s_nk;
+  const int nk = __popc(kmask);
   const int nchunk = (cin4 + KCT - 1) / KCT;
   const int T = nk * nchunk;  // pipeline slabs of this CTA
 
   if (producer) {
     // ---------------------------------------------------------------- producers
-    const int rowA = tid & (TMR - 1), jq0 = tid >> 7;            // items (rowA, jq0) and (rowA, jq0 + 2)
+    // lanes run along the channels of a row: 4 consecutive lanes read one row's 64 contiguous bytes (1 L1 wavefront
+    // per row instead of one per 16-byte item); this thread owns items (rowA, jqA) and (rowA + 64, jqA)
+    const int rowA = tid >> 2, jqA = tid & 3;
     const int nb_items = (KCT / 4) * nt;                         // float4 items of the weight slab
     float4 a_reg[2], bh_reg[2], bl_reg[2];
     // loop-invariant parts of this thread's two weight-slab items
@@ -174,16 +180,16 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
       b_jq[i] = b_on[i] ? e / nt : 0;
       b_n[i] = b_on[i] ? e - b_jq[i] * nt : 0;
     }
-    int ld_ki = 0, ld_c = 0;  // (active-offset index, channel slab) of the next slab to load
+    unsigned ld_rem = kmask;   // offsets still to load (lowest set bit = current one)
+    int ld_c = 0;              // channel slab of the next slab to load
     auto issue_loads = [&]() {
-      const int k = s_klist[ld_ki], c = ld_c;
-      const int src = s_nbr[k * TMR + rowA];
-      const float* arow = in + (size_t)src * ld_in + c * KCT;
+      const int k = __ffs(ld_rem) - 1, c = ld_c;
+      const int colq = c * KCT + jqA * 4;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int colq = (jq0 + 2 * i) * 4;
-        a_reg[i] = (src >= 0 && c * KCT + colq < cin4) ? __ldg(reinterpret_cast<const float4*>(arow + colq))
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int src = s_nbr[k * NBS + rowA + 64 * i];
+        a_reg[i] = (src >= 0 && colq < cin4) ? __ldg(reinterpret_cast<const float4*>(in + (size_t)src * ld_in + colq))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const size_t wbase = ((size_t)k * nq + (size_t)c * (KCT / 4)) * npad + col0;
 #pragma unroll
@@ -196,7 +202,7 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
           if (PREC == 3) bl_reg[i] = __ldg(reinterpret_cast<const float4*>(w_lo + off));
         }
       }
-      if (++ld_c == nchunk) { ld_c = 0; ++ld_ki; }
+      if (++ld_c == nchunk) { ld_c = 0; ld_rem &= ld_rem - 1; }
     };
     if (T > 0) issue_loads();
     for (int t = 0; t < T; ++t) {
@@ -214,8 +220,8 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
       for (int i = 0; i < 2; ++i) {
         const float4 v = a_cur[i];
         const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
-        a_hi[(jq0 + 2 * i) * TMR + rowA] = h;
-        if (PREC == 3) a_lo[(jq0 + 2 * i) * TMR + rowA] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        a_hi[jqA * APL + rowA + 64 * i] = h;
+        if (PREC == 3) a_lo[jqA * APL + rowA + 64 * i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -241,13 +247,13 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
       const uint32_t sb_hi = sbase + (PREC == 3 ? 2 : 1) * a_bytes, sb_lo = sb_hi + b_bytes;
 #pragma unroll
       for (int kk = 0; kk < KCT / 8; ++kk) {
-        const uint32_t a_off = kk * 2 * TMR * 16, b_off = kk * 2 * nt * 16;
-        const uint64_t dah = umma_desc(sa_hi + a_off, TMR * 16, 128), dbh = umma_desc(sb_hi + b_off, nt * 16, 128);
+        const uint32_t a_off = kk * 2 * APL * 16, b_off = kk * 2 * nt * 16;
+        const uint64_t dah = umma_desc(sa_hi + a_off, APL * 16, 128), dbh = umma_desc(sb_hi + b_off, nt * 16, 128);
         const int am = (PREC == 3) ? ((t * (KCT / 8) + kk) % 3) : 0;
         umma_tf32(tmem_d + am * nt, dah, dbh, idesc, (used >> am) & 1u);
         used |= 1u << am;
         if (PREC == 3) {
-          const uint64_t dal = umma_desc(sa_lo + a_off, TMR * 16, 128), dbl = umma_desc(sb_lo + b_off, nt * 16, 128);
+          const uint64_t dal = umma_desc(sa_lo + a_off, APL * 16, 128), dbl = umma_desc(sb_lo + b_off, nt * 16, 128);
           umma_tf32(tmem_d + 3 * nt, dal, dbh, idesc, (used >> 3) & 1u);
           used |= 1u << 3;
           umma_tf32(tmem_d + 3 * nt, dah, dbl, idesc, 1u);
@@ -420,8 +426,8 @@ int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, in
   if (K > 27) return EP_ERR_UNSUPPORTED;
   const int tmem_cols = pow2_cols((prec == 3 ? 4 : 1) * nt);
   if (tmem_cols > 512) return EP_ERR_UNSUPPORTED;
-  const size_t stage = (size_t)(prec == 3 ? 2 : 1) * ((KCT / 4) * TMR * 16 + (KCT / 4) * nt * 16);
-  const size_t smem = stage * NSTAGE + (size_t)K * TMR * sizeof(int);
+  const size_t stage = (size_t)(prec == 3 ? 2 : 1) * ((KCT / 4) * APL * 16 + (KCT / 4) * nt * 16);
+  const size_t smem = stage * NSTAGE + (size_t)K * NBS * sizeof(int);
   cudaError_t e;
   if (prec == 3) e = cudaFuncSetAttribute(spconv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   else e = cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
