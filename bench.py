@@ -33,6 +33,10 @@ FULL_OVER_SAMPLE = 31.0
 FULL_NOTE = ("value / 31: the oracle's full 3-level fragment took 130 s vs 4.2 s for this sample on the 8-core build container; "
              "level 2 (210 k candidate voxels) is skipped in the timed sample to keep the run within minutes")
 METRIC = "fragments/sec (9x640x480, 3-level 96^3)"
+DEFAULT_STREAMS = 4   # fragments in flight per GPU (EPRECON_STREAMS overrides)
+# dram__bytes_read.sum + dram__bytes_write.sum of one level-2 spconv_tc_kernel<3> launch (ncu --set full)
+SPCONV_TRAFFIC = {"bytes": 41.3e6, "note": "dram read+write bytes of one level-2 launch (74->8 ch, 200k rows) from "
+                                           "profiles/r01_spconv_tc_v2_ncu_summary.csv"}
 WORKLOAD = "configs[1]: single 9-view 640x480 fragment, 3-level 24/48/96^3 @4cm, GRU fusion (fresh scene), TSDF+occ heads"
 
 
@@ -132,19 +136,11 @@ class PackedHost:
             return ("d", {k: self._scan(v) for k, v in obj.items()})
         return ("v", obj)
 
-    def to_device(self, dev, reuse=False):
-        """reuse=True: copy into one of two persistent device staging buffers (no allocator traffic in the timed loop)."""
-        if reuse:
-            if not hasattr(self, "_stage"):
-                self._stage = [{dt: torch.empty_like(b, device=dev) for dt, b in self.bufs.items()} for _ in range(2)]
-                self._flip = 0
-            self._flip ^= 1
-            dbuf = self._stage[self._flip]
-            for dt, b in self.bufs.items():
-                dbuf[dt].copy_(b, non_blocking=True)
-        else:
-            dbuf = {dt: b.to(dev, non_blocking=True) for dt, b in self.bufs.items()}
+    def to_device(self, dev):
+        return self.build({dt: b.to(dev, non_blocking=True) for dt, b in self.bufs.items()})
 
+    def build(self, dbuf):
+        """Rebuild the nested structure as views into the per-dtype device buffers `dbuf`."""
         def build(sp):
             if sp[0] == "t":
                 _, dt, shape, off = sp
@@ -227,11 +223,30 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------ ours
+class DeviceStage:
+    """Per-stream device staging of a PackedHost: two persistent buffer sets, one cudaMemcpyAsync per dtype per step."""
+
+    def __init__(self, host, dev):
+        self.host = host
+        self.sets = [{dt: torch.empty_like(b, device=dev) for dt, b in host.bufs.items()} for _ in range(2)]
+        self.flip = 0
+
+    def load(self):
+        self.flip ^= 1
+        dbuf = self.sets[self.flip]
+        for dt, b in self.host.bufs.items():
+            dbuf[dt].copy_(b, non_blocking=True)
+        return self.host.build(dbuf)
+
+
 def run_ours(args):
+    import queue
+
     import torch.distributed as dist
     from eprecon_b200 import _lib, ops, synth
     from eprecon_b200.dist import gather_fragments, merge_substitute
     from eprecon_b200.neucon_network import NeuConNet
+    from eprecon_b200.streams import FragmentStreams
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -242,6 +257,8 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    K = args.steps
+    S = max(1, int(os.environ.get("EPRECON_STREAMS", str(DEFAULT_STREAMS))))   # fragments in flight per GPU
 
     cfg = synth.make_cfg()
     cfg.THRESHOLDS = list(synth.BENCH_THRESHOLDS)
@@ -249,110 +266,174 @@ def run_ours(args):
     synth.fill_parameters_(net, 1)
     net = net.to(dev)
     net.train()  # the reference evaluates in train mode (main.py:357): batch-statistics BN, training-time caps live
+    fs = FragmentStreams(net, S, dev)   # S replicas over the same weights, one host thread + CUDA stream each
 
-    inputs, fa, fb = synth.make_fragment(seed=1)   # every rank: its own copy of the same-shape fragment (weak scaling)
+    inputs, fa, fb = synth.make_fragment(seed=1)   # every rank / stream: its own copy of the same-shape fragment (weak scaling)
     host = PackedHost({"inputs": {k: v for k, v in inputs.items() if torch.is_tensor(v) or isinstance(v, list) and torch.is_tensor(v[0])},
                        "fa": fa, "fb": fb})
-    n_copies = 4   # rotate over 4 resident copies of the inputs: 4 x 54 MB of feature maps > 126 MB L2
+    n_copies = max(4, S + 1)   # rotate over >= 4 resident copies of the inputs: 4 x 54 MB of feature maps > 126 MB L2
     resident = [host.to_device(dev) for _ in range(n_copies)]
     torch.cuda.synchronize()
     h2d_bytes = host.nbytes
     rel = ((inputs["vol_origin_partial"][0] - inputs["vol_origin"][0]) / cfg.VOXEL_SIZE).long()
+    rel_dev = rel.to(dev).to(torch.int32)
+    uid = [0]
 
-    step_id = [0]
-
-    def one_step(dev_in, exchange=True):
-        step_id[0] += 1
+    def fragment(net_r, dev_in, tag):
         ins = dict(dev_in["inputs"])
-        ins["scene"] = [f"scene_r{rank}_{step_id[0]}"]   # fresh scene -> GRU state reset -> identical work every step
-        ins["fragment"] = [f"frag_{step_id[0]}"]
-        out, _ = net(dev_in["fa"], dev_in["fb"], ins, {})
+        ins["scene"] = [f"scene_r{rank}_{tag}"]   # fresh scene -> GRU state reset -> identical work every fragment
+        ins["fragment"] = [f"frag_{tag}"]
+        out, _ = net_r(dev_in["fa"], dev_in["fb"], ins, {})
         assert "coords" in out, "forward early-returned (degenerate fragment)"
-        if world > 1 and exchange:
-            gc = out["coords"][:, 1:].to(torch.int32) + rel.to(dev).to(torch.int32) + rank * 24  # scenes side by side
-            frags = gather_fragments(gc, out["tsdf"].view(-1))
-            boxes = [((rel + r * 24).tolist(), (rel + r * 24 + torch.tensor(cfg.N_VOX)).tolist()) for r in range(world)]
-            out["scene_coords"], out["scene_tsdf"] = merge_substitute(frags, boxes)
         return out
+
+    def exchange(outs):
+        """The one exchange of the path (configs[3]): NCCL gather + merge of the step's sparse TSDFs (main thread / stream)."""
+        gcs, tss, boxes = [], [], []
+        for s, o in enumerate(outs):
+            off = (rank * S + s) * 24            # scenes side by side along x
+            shift = rel_dev.clone()
+            shift[0] += off
+            gcs.append(o["coords"][:, 1:].to(torch.int32) + shift)
+            tss.append(o["tsdf"].view(-1))
+        frags = gather_fragments(torch.cat(gcs), torch.cat(tss))
+        for r in range(world):
+            lo = rel.clone()
+            lo[0] += r * S * 24
+            hi = rel + torch.tensor(cfg.N_VOX)
+            hi[0] += (r * S + S - 1) * 24
+            boxes.append((lo.tolist(), hi.tolist()))
+        return merge_substitute(frags, boxes)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(n_steps, body):
+        """Every stream runs `n_steps` fragments back to back (no inter-step barrier); the main thread does the per-step
+        exchange when world > 1.  Device-timed between two full synchronisations; returns ms."""
+        done = queue.SimpleQueue()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+
+        def job(slot):
+            def run(net_r, stream):
+                stream.wait_event(e0)
+                for k in range(n_steps):
+                    uid[0] += 1
+                    out = body(net_r, slot, k, f"s{slot}_{uid[0]}")
+                    if world > 1:
+                        ev = torch.cuda.Event()
+                        ev.record(stream)
+                        done.put((k, slot, out, ev))
+                stream.synchronize()
+            return run
+        futs = [fs.submit(s, job(s)) for s in range(S)]
+        if world > 1:
+            pending = {}
+            main = torch.cuda.current_stream()
+            for k in range(n_steps):
+                while len(pending.get(k, {})) < S:
+                    kk, slot, out, ev = done.get()
+                    pending.setdefault(kk, {})[slot] = (out, ev)
+                outs = []
+                for s in range(S):
+                    out, ev = pending[k][s]
+                    main.wait_event(ev)
+                    for t in (out["coords"], out["tsdf"]):
+                        t.record_stream(main)
+                    outs.append(out)
+                exchange(outs)
+                del pending[k]
+        for f in futs:
+            f.result()
+        torch.cuda.synchronize()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()   # started before the warm-up so that its process start-up stays out of the timed region
-    for w in range(max(args.warmup, 3)):
-        one_step(resident[w % n_copies])
-    barrier()
+    # warm-up: first each replica alone (graph capture, lazily built constant tables), then W concurrent steps
+    fs.warm(lambda net_r, stream: fragment(net_r, resident[0], f"warm{id(net_r)}"))
+    W = max(args.warmup, 3)
+    run_steps(W, lambda net_r, slot, k, tag: fragment(net_r, resident[(k * S + slot) % n_copies], tag))
     if rank == 0:
         sampler.rows.clear()   # keep only samples taken under load (timed region + e2e loop)
 
-    # ---- timed region: EXACTLY K steps, CUDA events on the launching stream, max over ranks
-    ops.PROFILE = {"mode": "events"}
-    _lib.LAUNCHES["n"] = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for k in range(args.steps):
-        out = one_step(resident[k % n_copies])
-    e1.record()
-    barrier()
-    launches = _lib.LAUNCHES["n"]
-    prof, ops.PROFILE = ops.PROFILE, None
-    clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * args.steps / (ms / 1e3)
+    # ---- timed region: EXACTLY K steps of S fragments each, device-timed, max over ranks
+    ms = run_steps(K, lambda net_r, slot, k, tag: fragment(net_r, resident[(k * S + slot) % n_copies], tag))
+    value = world * S * K / (ms / 1e3)
 
-    # ---- e2e: host (pinned) inputs -> H2D -> forward -> D2H of the sparse TSDF, every step
-    coords_h = torch.empty((200000, 4), dtype=torch.int64).pin_memory()
-    tsdf_h = torch.empty((200000, 1), dtype=torch.float32).pin_memory()
+    # ---- e2e: host (pinned) inputs -> H2D -> forward -> D2H of the sparse TSDF, every fragment, on its own stream
+    stages = [DeviceStage(host, dev) for _ in range(S)]
+    coords_h = [torch.empty((200000, 4), dtype=torch.int64).pin_memory() for _ in range(S)]
+    tsdf_h = [torch.empty((200000, 1), dtype=torch.float32).pin_memory() for _ in range(S)]
     d2h = [0]
 
-    h2d_ev = []
-
-    def e2e_step():
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record()
-        dev_in = host.to_device(dev, reuse=True)   # one pinned->device copy per dtype (fp32 features/matrices, bool GT occupancy)
-        eb.record()
-        h2d_ev.append((ea, eb))
-        o = one_step(dev_in)
+    def e2e_fragment(net_r, slot, k, tag):
+        dev_in = stages[slot].load()   # one pinned->device copy per dtype (fp32 features/matrices, bool GT occupancy)
+        o = fragment(net_r, dev_in, tag)
         n = o["coords"].shape[0]
-        coords_h[:n].copy_(o["coords"], non_blocking=True)
-        tsdf_h[:n].copy_(o["tsdf"], non_blocking=True)
+        coords_h[slot][:n].copy_(o["coords"], non_blocking=True)
+        tsdf_h[slot][:n].copy_(o["tsdf"], non_blocking=True)
         d2h[0] = n * (4 * 8 + 4)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream().synchronize()   # the caller holds the result on the host before the next fragment
+        return o
 
-    e2e_step()
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    t1.record()
-    barrier()
-    ms_e2e = t0.elapsed_time(t1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    e2e_value = world * args.steps / (ms_e2e / 1e3)
+    run_steps(1, e2e_fragment)
+    ms_e2e = run_steps(K, e2e_fragment)
+    e2e_value = world * S * K / (ms_e2e / 1e3)
+    clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel family: per-launch CUDA-event durations from the timed region + an untimed
-    #      pass that counts each launch's algorithmic work (same deterministic launch sequence)
+    # ---- single-stream pass on the main thread: latency of one fragment, per-launch CUDA-event durations of the two
+    #      dominant kernel families (events around every launch would perturb the multi-stream timed region, and a
+    #      kernel sharing the SMs with other streams has no roofline of its own), launch count, algorithmic work
     roofline = None
     kernel_share = {}
+    single = None
+    launches_per_fragment = None
     if rank == 0:
-        ops.PROFILE = {"mode": "work"}
-        one_step(resident[0], exchange=False)
+        net0 = fs.nets[0]
+        for w in range(2):
+            fragment(net0, resident[w], f"single_warm{w}")
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for k in range(K):
+            fragment(net0, resident[k % n_copies], f"single{k}")
+        eb.record()
+        torch.cuda.synchronize()
+        single_ms = ea.elapsed_time(eb) / K
+        single = {"ms_per_fragment": single_ms, "fragments_per_s": 1e3 / single_ms,
+                  "note": "one fragment at a time on one stream (latency view of the same step)"}
+        # launch count of one fragment on the shipped (native-executor) path
+        _lib.LAUNCHES["n"] = 0
+        fragment(net0, resident[0], "count")
+        torch.cuda.synchronize()
+        launches_per_fragment = _lib.LAUNCHES["n"]
+        # per-launch events need the per-kernel Python programs (the native executor issues the very same launches
+        # from C++, where bench.py cannot bracket them): same kernels, same arguments, same order
+        from eprecon_b200 import executor
+        exec_was, executor.ENABLED = executor.ENABLED, False
+        fragment(net0, resident[1], "prof_warm")
+        ops.PROFILE = {"mode": "events"}
+        for k in range(K):
+            fragment(net0, resident[k % n_copies], f"prof{k}")
+        torch.cuda.synchronize()
+        prof_ms = single_ms * K
+        prof, ops.PROFILE = ops.PROFILE, {"mode": "work"}
+        fragment(net0, resident[0], "work")
         work, ops.PROFILE = ops.PROFILE, None
+        executor.ENABLED = exec_was
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -363,18 +444,21 @@ def run_ours(args):
             evs = prof.get(kind, [])
             tot_ms = sum(a.elapsed_time(b) for a, b in evs)
             fam[kind] = {"launches": len(evs), "ms": tot_ms}
-            kernel_share[kind] = {"launches_per_step": len(evs) // max(args.steps, 1), "ms_per_step": tot_ms / args.steps,
-                                  "share_of_step": tot_ms / ms if ms else None}
+            kernel_share[kind] = {"launches_per_fragment": len(evs) // max(K, 1), "ms_per_fragment": tot_ms / K,
+                                  "share_of_single_stream_step": tot_ms / prof_ms if prof_ms else None}
         per_step = len(work.get("spconv_work", []))
         flops = sum(2.0 * w["cin"] * w["cout"] * w["pairs"] for w in work.get("spconv_work", []))
         sp_bytes = sum(4.0 * (w["m_in"] * w["cin"] + w["m_out"] * w["cout"] + w["K"] * w["cin"] * w["cout"] + w["pairs"])
                        for w in work.get("spconv_work", []))
         bp_bytes = sum(w["bytes"] for w in work.get("bp_gather_work", []))
-        sp_ms = fam["spconv"]["ms"] / args.steps
-        bp_ms = fam["bp_gather"]["ms"] / args.steps
+        sp_ms = fam["spconv"]["ms"] / K
+        bp_ms = fam["bp_gather"]["ms"] / K
         tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         src = "of measured (MEASURED_PEAKS.json)" if peaks else "of fallback (B200_PROFILING.md)"
+        where = ("per-launch CUDA events on the launching stream over K single-stream fragments run right after the timed "
+                 "region (same step, same inputs; launches issued by the per-kernel Python programs so that each one can "
+                 "be bracketed); shares are relative to the single-stream step of the shipped path")
         if sp_ms >= bp_ms:
             ach = flops / (sp_ms * 1e-3) / 1e12 if sp_ms else 0.0
             impl = ops.SPCONV_IMPL
@@ -383,24 +467,24 @@ def run_ours(args):
                      "ffma": "spconv_kernel (gather-GEMM, fp32 FFMA)"}[impl]
             roofline = {"kernel": kname + "; K=1 linears run on spconv_kernel (fp32 FFMA)", "bound": "tensor", "achieved": ach,
                         "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak,
-                        "traffic": 41.3e6 if impl != "ffma" else None,
-                        "traffic_note": "dram read+write bytes of one level-2 launch (74->8 ch, 200k rows) from profiles/r01_spconv_tc_v2_ncu_summary.csv",
+                        "traffic": SPCONV_TRAFFIC["bytes"] if impl != "ffma" else None,
+                        "traffic_note": SPCONV_TRAFFIC["note"], "measured": where,
                         "peak_source": src + ", bf16 dense sustained (tf32 dense peak is half of it); achieved counts the "
                                              "algorithmic 2*Cin*Cout*pairs flops once (3xTF32 issues 3 MMAs per product); the kernel is "
                                              "gather/L2-bound, see memory_view",
                         "memory_view": {"achieved_GBs": sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms else None, "peak_GBs": hbm_peak,
                                         "frac": (sp_bytes / (sp_ms * 1e-3) / 1e9 / hbm_peak) if sp_ms else None,
                                         "bytes": "4(M_in*Cin + M_out*Cout) + 4*K*Cin*Cout + 4*pairs per launch (lower bound: every input row read once)"},
-                        "launches_per_step": per_step, "algorithmic_flops_per_step": flops,
-                        "algorithmic_bytes_per_step": sp_bytes, "avg_launch_us": 1e3 * sp_ms / max(per_step, 1)}
+                        "launches_per_fragment": per_step, "algorithmic_flops_per_fragment": flops,
+                        "algorithmic_bytes_per_fragment": sp_bytes, "avg_launch_us": 1e3 * sp_ms / max(per_step, 1)}
         else:
             ach = bp_bytes / (bp_ms * 1e-3) / 1e9 if bp_ms else 0.0
-            roofline = {"kernel": "bp_gather_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "peak_source": src,
-                        "algorithmic_bytes_per_step": bp_bytes}
+            roofline = {"kernel": "bp_fused_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak, "traffic": None, "peak_source": src, "measured": where,
+                        "algorithmic_bytes_per_fragment": bp_bytes}
         roofline["back_projection"] = {"achieved_GBs": bp_bytes / (bp_ms * 1e-3) / 1e9 if bp_ms else None, "peak_GBs": hbm_peak,
                                        "frac": (bp_bytes / (bp_ms * 1e-3) / 1e9 / hbm_peak) if bp_ms else None,
-                                       "algorithmic_bytes_per_step": bp_bytes, "gather_ms_per_step": bp_ms}
+                                       "algorithmic_bytes_per_fragment": bp_bytes, "ms_per_fragment": bp_ms}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not os.environ.get("EPRECON_BENCH_SKIP_CPU"):
@@ -413,17 +497,21 @@ def run_ours(args):
 
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "fragments/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": value, "unit": "fragments/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sizes": net.last_sizes, "thresholds": cfg.THRESHOLDS,
-                       "l2": "inputs rotated over 4 HBM-resident copies (216 MB of feature maps > 126 MB L2)",
-                       "multi_gpu": "one fragment per rank + NCCL all_gather/merge of the global sparse TSDF per step" if world > 1 else "n/a"},
-            "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h[0],
-                    "ms_per_step": ms_e2e / args.steps,
-                    "h2d_ms_per_step": sum(a.elapsed_time(b) for a, b in h2d_ev[1:]) / max(len(h2d_ev) - 1, 1)},
-            "gpu_launches": launches, "gpu_launches_per_step": launches // max(args.steps, 1),
+            "config": {"workload": WORKLOAD, "fragments_per_step": S * world,
+                       "streams_per_gpu": S, "step": f"{S} independent fragments in flight per GPU (one CUDA stream + host thread each, "
+                                                     "shared weights); value = fragments completed / device time",
+                       "sizes": fs.nets[0].last_sizes, "thresholds": cfg.THRESHOLDS,
+                       "l2": f"inputs rotated over {n_copies} HBM-resident copies ({n_copies * 54} MB of feature maps > 126 MB L2)",
+                       "multi_gpu": f"{S} fragments per rank per step + NCCL all_gather/merge of the step's global sparse TSDF" if world > 1 else "n/a"},
+            "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": h2d_bytes * S, "d2h_bytes_per_step": d2h[0] * S,
+                    "ms_per_step": ms_e2e / K},
+            "single_stream": single,
+            "gpu_launches": (launches_per_fragment or 0) * S * K, "gpu_launches_per_fragment": launches_per_fragment,
             "clocks": clocks, "roofline": roofline, "kernel_share": kernel_share, "cpu_baseline": cpu_baseline}))
+    fs.close()
     if world > 1:
         dist.destroy_process_group()
 

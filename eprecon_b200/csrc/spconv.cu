@@ -181,17 +181,17 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
 
 // reduce per-CTA partials in CTA order (double accumulation) -> scale/shift of train-mode BatchNorm:
 //   y = (x - mean) * rsqrt(var_biased + eps) * gamma + beta  ==  x * scale + shift
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ bn_partial, int nblk, int c, int m, float eps,
                    const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ scale_shift /*[2,c]*/, float* __restrict__ mean_var /*[2,c] or null*/) {
-  // 32 columns x 8 tile-lanes per CTA: lane ty sums tiles ty, ty+8, ... (double), then a fixed-order combine
-  __shared__ double s_s[8][33], s_q[8][33];
+  // 32 columns x 32 tile-lanes per CTA: lane ty sums tiles ty, ty+32, ... (double), then a fixed-order combine
+  __shared__ double s_s[32][33], s_q[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
   double s = 0.0, q = 0.0;
   if (col < c)
-    for (int b = ty; b < nblk; b += 8) {
+    for (int b = ty; b < nblk; b += 32) {
       s += (double)bn_partial[((size_t)b * 2 + 0) * c + col];
       q += (double)bn_partial[((size_t)b * 2 + 1) * c + col];
     }
@@ -200,7 +200,7 @@ bn_finalize_kernel(const float* __restrict__ bn_partial, int nblk, int c, int m,
   __syncthreads();
   if (ty != 0 || col >= c) return;
 #pragma unroll
-  for (int r = 1; r < 8; ++r) { s += s_s[r][tx]; q += s_q[r][tx]; }
+  for (int r = 1; r < 32; ++r) { s += s_s[r][tx]; q += s_q[r][tx]; }
   const double mean = s / m;
   double var = q / m - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -249,7 +249,7 @@ int ep_colstats(const float* x, int ld, int64_t m, int c, float* bn_partial, cud
 int ep_bn_finalize(const float* bn_partial, int num_row_tiles, int c, int64_t m, float eps, const float* gamma,
                    const float* beta, float* scale_shift, float* mean_var, cudaStream_t stream) {
   if (num_row_tiles < 1 || c < 1 || m < 1) return EP_ERR_ARG;
-  bn_finalize_kernel<<<ep_div_up(c, 32), 256, 0, stream>>>(bn_partial, num_row_tiles, c, (int)m, eps, gamma, beta,
+  bn_finalize_kernel<<<ep_div_up(c, 32), 1024, 0, stream>>>(bn_partial, num_row_tiles, c, (int)m, eps, gamma, beta,
                                                            scale_shift, mean_var);
   EP_CHECK_LAUNCH();
   return EP_OK;

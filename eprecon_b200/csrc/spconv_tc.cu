@@ -344,37 +344,56 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
   }
 }
 
-// out[row, col] = bias + sum_z partial[z][row][col] (fixed z order), plus the per-64-row-tile BN statistics
+// out[row, col] = bias + sum_z partial[z][row][col] (fixed z order), plus the per-64-row-tile BN statistics.
+// One CTA per 64-row tile; 256 threads = 8 row lanes x 32 float4 column lanes, so a thread has 8 x splits independent
+// 16-byte loads in flight (the first version walked 16 rows x splits scalar loads per thread: 34 us per launch, as
+// long as the convolution it finished).
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, int m_out, int npad, int cout,
                      const float* __restrict__ bias, float* __restrict__ out, int ld_out, float* __restrict__ bn_partial) {
-  __shared__ float s_s[4][64], s_q[4][64];
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 columns x 4 row groups of 16 rows
+  __shared__ float s_s[8][128], s_q[8][128];
+  const int cq = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int row0 = blockIdx.x * 64;
-  for (int c0 = 0; c0 < cout; c0 += 64) {
-    const int col = c0 + tx;
-    float s = 0.f, q = 0.f;
-    if (col < cout) {
-      const float bv = bias ? bias[col] : 0.f;
-      for (int r = 0; r < 16; ++r) {
-        const int row = row0 + ty * 16 + r;
+  const size_t plane = (size_t)m_out * npad;
+  for (int c0 = 0; c0 < cout; c0 += 128) {
+    const int col = c0 + cq * 4;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    if (col < npad && col < cout) {
+      float bv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = (bias && col + j < cout) ? bias[col + j] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + ry + 8 * i;
         if (row < m_out) {
-          float v = 0.f;
-          for (int z = 0; z < splits; ++z) v += partial[((size_t)z * m_out + row) * npad + col];
-          v += bv;
-          out[(size_t)row * ld_out + col] = v;
-          s += v;
-          q = fmaf(v, v, q);
+          const float* p = partial + (size_t)row * npad + col;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int z = 0; z < splits; ++z) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p + (size_t)z * plane));
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+          }
+          const float r[4] = {v.x + bv[0], v.y + bv[1], v.z + bv[2], v.w + bv[3]};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col + j < cout) {
+              out[(size_t)row * ld_out + col + j] = r[j];
+              s[j] += r[j];
+              q[j] = fmaf(r[j], r[j], q[j]);
+            }
         }
       }
     }
     if (bn_partial) {
-      s_s[ty][tx] = s;
-      s_q[ty][tx] = q;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s_s[ry][cq * 4 + j] = s[j]; s_q[ry][cq * 4 + j] = q[j]; }
       __syncthreads();
-      if (ty == 0 && col < cout) {
-        bn_partial[((size_t)blockIdx.x * 2 + 0) * cout + col] = (s_s[0][tx] + s_s[1][tx]) + (s_s[2][tx] + s_s[3][tx]);
-        bn_partial[((size_t)blockIdx.x * 2 + 1) * cout + col] = (s_q[0][tx] + s_q[1][tx]) + (s_q[2][tx] + s_q[3][tx]);
+      if (threadIdx.x < 128 && c0 + (int)threadIdx.x < cout) {
+        const int t = threadIdx.x;
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { a += s_s[r][t]; b += s_q[r][t]; }   // fixed order: deterministic
+        bn_partial[((size_t)blockIdx.x * 2 + 0) * cout + c0 + t] = a;
+        bn_partial[((size_t)blockIdx.x * 2 + 1) * cout + c0 + t] = b;
       }
       __syncthreads();
     }

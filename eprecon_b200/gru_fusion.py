@@ -13,7 +13,7 @@ prediction" guard, models/neucon_network.py:486-490) stays a small dense 1-chann
 import torch
 import torch.nn as nn
 
-from . import _lib, ops, sparse
+from . import _lib, executor, ops, sparse
 from .modules import ConvGRU
 from .ops import stream_ptr
 
@@ -208,11 +208,15 @@ class GRUFusion(nn.Module):
                 upd0[:, 0] = 0
                 r_coords = ops.aligned_coords(upd0, org, voxel_size, w2ac, zero_batch=True)
                 gru_v, gru_i = self.fusion_nets_voxel[scale], self.fusion_nets_img[scale]
-                pc1 = sparse.PointCloud(r_coords, gru_v.vres)
-                pc2 = sparse.PointCloud(pc1.scaled, gru_v.vres, order="hash")
-                out_v = gru_v.run(gvalues[:, :cv], values[:, :cv], pc1, pc2)
-                out_i = gru_i.run(gvalues[:, cv:c_all], values[:, cv:c_all], pc1, pc2)
-                values = torch.cat([out_v[:, :cv], out_i[:, :c_all - cv]], dim=-1)
+                if executor.enabled() and c_all % 4 == 0 and cv % 4 == 0:
+                    # both ConvGRUs of the level on shared voxelisations as ONE native call (csrc/executor.cu)
+                    values = executor.gru_level(self, gru_v, gru_i, r_coords, gvalues, values, cv, c_all)
+                else:
+                    pc1 = sparse.PointCloud(r_coords, gru_v.vres)
+                    pc2 = sparse.PointCloud(pc1.scaled, gru_v.vres, order="hash")
+                    out_v = gru_v.run(gvalues[:, :cv], values[:, :cv], pc1, pc2)
+                    out_i = gru_i.run(gvalues[:, cv:c_all], values[:, cv:c_all], pc1, pc2)
+                    values = torch.cat([out_v[:, :cv], out_i[:, :c_all - cv]], dim=-1)
             # update_map (gru_fusion.py:195-204): drop in-volume global rows, append the fused ones
             relt = self._const(tuple(rel), dev, torch.int32)
             vpad = values if values.shape[1] == g["F"].shape[1] else torch.nn.functional.pad(

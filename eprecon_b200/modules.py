@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops, sparse
+from . import executor, ops, sparse
 from .ops import ceil4
 from .tensor import PointTensor  # noqa: F401  (re-exported for callers that build inputs)
 
@@ -168,6 +168,8 @@ class SPVCNN(nn.Module):
             padded = torch.zeros((feat.shape[0], ceil4(self.in_channels)), dtype=torch.float32, device=feat.device)
             padded[:, :self.in_channels] = feat
             feat = padded
+        if executor.enabled():   # the whole program below as ONE native call (csrc/executor.cu)
+            return executor.spvcnn(self, feat, z.C.float().contiguous())
         pc = sparse.PointCloud(z.C.float().contiguous(), self.vres)
         v0 = pc.vox
         x0 = pc.voxelize(feat, self.in_channels)                                  # initial_voxelize
@@ -430,6 +432,8 @@ class Linear4xTrans(nn.Module):
     def forward(self, x):
         c = self.C_in
         xr = _as_rows(x, c)
+        if executor.enabled():
+            return executor.linear4x(self, [self], xr)[0]
         y, _ = linear(xr, self.linear1, self._p[0])
         ops.layernorm(y, 4 * c, self.norm1.weight.detach(), self.norm1.bias.detach(), relu_after=True, eps=self.norm1.eps)
         y, _ = linear(y, self.linear2, self._p[1])

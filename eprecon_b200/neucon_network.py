@@ -23,7 +23,7 @@ except Exception:  # pragma: no cover
     import logging
     logger = logging.getLogger("eprecon_b200")
 
-from . import _lib, ops
+from . import _lib, executor, ops
 from .gru_fusion import GRUFusion
 from .modules import SPVCNN, Linear4xTrans, Panoptic_Feat_Fusion
 from .occupancy_initialization import Back_Project, Occupancy_Initialization
@@ -195,8 +195,11 @@ class NeuConNet(nn.Module):
             feat_all[:, cv:] = feat[:, :c_img]
             up_coords, feat_all, tsdf_target, occ_target = self.gru_fusion(up_coords, feat_all, inputs, i)
             feat_v = feat_all[:, :cv]
-            tsdf = self.tsdf_preds[i](feat_v)
-            occ = self.occ_preds[i](feat_v)
+            if executor.enabled() and feat_v.stride(0) % 4 == 0:
+                tsdf, occ = executor.linear4x(self, [self.tsdf_preds[i], self.occ_preds[i]], feat_v)   # both heads, one call
+            else:
+                tsdf = self.tsdf_preds[i](feat_v)
+                occ = self.occ_preds[i](feat_v)
             loss_dict[f"tsdf_occ_loss_{i}"] = self._zero_loss(origin)
 
             # ------------------------------------------------ sparsity for the next level (:454-507)

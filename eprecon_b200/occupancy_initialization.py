@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import executor, ops
 from .modules import (Conv2d_Block, Conv2d_Residual_Block, Fusion_Block, Spares3dELAN, SparseSubMConv3d, SubMSites,
                       _as_rows)
 
@@ -133,9 +133,12 @@ class Occupancy_Initialization(nn.Module):
             sel = slice(None) if bs == 1 else torch.nonzero(kept[:, 0] == b).squeeze(1)
             cb = subm_coords[sel].clone()
             cb[:, 0] = 0
+            x = _as_rows(var[sel], d)
+            if executor.enabled():   # BN -> ELAN -> 3 residual SubM convs -> SubM 32->1 -> BN as ONE native call
+                occ_chunks.append(executor.init_head(self, x, cb.contiguous(), shape)[:, :1])
+                continue
             sites = SubMSites(cb, shape)
             m = cb.shape[0]
-            x = _as_rows(var[sel], d)
             x = ops.affine_act(x.clone(), d, ss_a=ops.bn_scale_shift(ops.colstats(x, d), m, self.norm0.weight.detach(),
                                                                   self.norm0.bias.detach(), self.norm0.eps))
             x = _as_rows(self.similary_1(x, cb, 1, shape, sites=sites), d)

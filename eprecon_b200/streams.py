@@ -1,0 +1,115 @@
+"""FragmentStreams — several fragments in flight on ONE GPU.
+
+A single fragment cannot fill a B200: the coarse levels launch 40-tile grids on 148 SMs, and every level ends in a
+handful of 4-byte size read-backs (the sparsity is data dependent) during which the device idles.  Fragments of
+different scenes are independent (the only shared state is the per-scene GRU volume,
+models/gru_fusion.py:31-38), so the data-parallel unit is "one scene stream per CUDA stream": S replicas of NeuConNet
+share one set of parameters but own their GRUFusion state, kernel-map caches and captured CUDA graphs; each replica
+is driven by its own host thread on its own stream, so one stream's read-back bubble is filled by the others'
+kernels.  The C ABI takes the stream explicitly and every ctypes / torch call releases the GIL, so plain threads work.
+
+A scene's fragments must stay on one replica and in order (the GRU recurrence): route by `slot`.
+"""
+import queue
+import sys
+import threading
+
+import torch
+
+__all__ = ["replicate", "FragmentStreams"]
+
+
+def replicate(net):
+    """A second NeuConNet over the SAME parameter / buffer storage as `net` (no weight copy) with private per-scene
+    state and caches."""
+    from .neucon_network import NeuConNet
+    rep = NeuConNet(net.cfg)
+    src_p, src_b = dict(net.named_parameters()), dict(net.named_buffers())
+    for name, p in rep.named_parameters():
+        p.data = src_p[name].data
+    for name, b in rep.named_buffers():
+        b.data = src_b[name].data
+    rep.train(net.training)
+    rep.with_panoptic_features = net.with_panoptic_features
+    return rep
+
+
+class _Future:
+    def __init__(self):
+        self._ev, self._val, self._exc = threading.Event(), None, None
+
+    def set(self, val=None, exc=None):
+        self._val, self._exc = val, exc
+        self._ev.set()
+
+    def result(self):
+        self._ev.wait()
+        if self._exc is not None:
+            raise self._exc
+        return self._val
+
+
+class FragmentStreams:
+    def __init__(self, net, n_streams, device=None):
+        assert n_streams >= 1
+        self.device = device if device is not None else next(net.parameters()).device
+        self.nets = [net] + [replicate(net) for _ in range(n_streams - 1)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        self._queues = [queue.SimpleQueue() for _ in range(n_streams)]
+        self._threads = []
+        if sys.getswitchinterval() > 5e-4:
+            sys.setswitchinterval(5e-4)   # host threads hand the GIL over at every launch; keep the fallback timer short
+        for i in range(n_streams):
+            t = threading.Thread(target=self._worker, args=(i,), daemon=True, name=f"eprecon-stream-{i}")
+            t.start()
+            self._threads.append(t)
+
+    def __len__(self):
+        return len(self.nets)
+
+    def _worker(self, i):
+        torch.cuda.set_device(self.device)
+        q = self._queues[i]
+        while True:
+            job = q.get()
+            if job is None:
+                return
+            fn, fut = job
+            try:
+                with torch.cuda.stream(self.streams[i]), torch.no_grad():
+                    fut.set(fn(self.nets[i], self.streams[i]))
+            except BaseException as e:  # surfaced by Future.result() on the submitting thread
+                fut.set(exc=e)
+
+    def submit(self, slot, fn):
+        """Run fn(net_replica, cuda_stream) on worker `slot` (its stream is current); returns a future."""
+        fut = _Future()
+        self._queues[slot].put((fn, fut))
+        return fut
+
+    def warm(self, fn):
+        """Run fn once per replica, ONE AFTER THE OTHER, then synchronise the device: CUDA-graph captures and the shared
+        lazily-built constant tables (kernel offsets, UMMA weight slabs) must exist before replicas run concurrently."""
+        for i in range(len(self.nets)):
+            self.submit(i, fn).result()
+            torch.cuda.synchronize(self.device)
+
+    def forward_many(self, fragments):
+        """fragments: list of (features, features_backbone2d_occ_pano, inputs, outputs); fragment j runs on replica
+        j % S.  Returns [(outputs, loss_dict)] in order (each replica's stream is synchronised)."""
+        s = len(self.nets)
+
+        def job(frag):
+            def run(net, stream):
+                res = net(*frag)
+                stream.synchronize()
+                return res
+            return run
+        futs = [self.submit(j % s, job(f)) for j, f in enumerate(fragments)]
+        return [f.result() for f in futs]
+
+    def close(self):
+        for q in self._queues:
+            q.put(None)
+        for t in self._threads:
+            t.join(timeout=5)

@@ -161,6 +161,39 @@ int ep_mark_parents(const int32_t* coords, int64_t n, int step, int dx, int dy, 
 int ep_lookup_marks(const int32_t* coords, int64_t n, int step, int dx, int dy, int dz, int bs, const uint8_t* vol,
                     uint8_t* flags, cudaStream_t stream);
 
+/* ---- small index helpers used by the native executor --------------------------------------------------------
+ * ep_csr_expand: segments of a (voxel id)-keyed sort -> dense per-voxel [s0, s1) ranges (s0/s1 pre-zeroed; the scatter
+ * the reference gets from torchsparse spcount/spvoxelize, ops/torchsparse_utils.py:51-58).  ep_translate_index:
+ * out[i] = idx[i] >= 0 ? rank[idx[i]] : -1 (the ConvGRU.convr stale-cache view, models/modules.py:216-217). */
+int ep_csr_expand(const uint64_t* keys_sorted, const int32_t* seg_start, const int32_t* seg_end, int64_t n_segments,
+                  int32_t* s0, int32_t* s1, cudaStream_t stream);
+int ep_translate_index(const int32_t* idx, int64_t n, const int32_t* rank, int32_t* out, cudaStream_t stream);
+
+/* ---- native executor: one call per reference module (csrc/executor.cu) -----------------------------------------
+ * Each function runs the complete launch program of one reference module forward() -- the same launchers, order and
+ * arguments as the Python mirrors in eprecon_b200/modules.py, bit-identical results -- with every temporary carved
+ * from the caller's scratch `arena` (256-byte aligned; EP_ERR_WORKSPACE if too small: grow and call again, the call
+ * has no side effects besides `out`).  UNLIKE the per-kernel entry points they synchronise `stream` at the
+ * data-dependent size read-backs (voxel counts).  `desc` / `globals`: flat int64 parameter descriptors, layout in
+ * eprecon_b200/executor.py.  `stats` (optional, int64[2]) receives the arena high-water mark and the launch count.
+ *   ep_exec_spvcnn     <- SPVCNN.forward               (models/modules.py:138-175)
+ *   ep_exec_gru_level  <- the two ConvGRU.forward of a GRUFusion level (models/gru_fusion.py:339-349, modules.py:200-222)
+ *   ep_exec_linear4x   <- Linear4xTrans.forward heads  (models/modules.py:298-311)
+ *   ep_exec_init_head  <- Occupancy_Initialization.forward sparse head (models/occupancy_initialization.py:131-176) */
+size_t ep_exec_launch_count(void);
+int ep_exec_desc_check(int kind, const int64_t* desc);   /* host-only descriptor validation, no GPU needed */
+int ep_exec_spvcnn(const int64_t* desc, const int64_t* globals, const float* pts, const float* feat, int ld_feat,
+                   int64_t n, float vres, float* out, int ld_out, void* arena, size_t arena_bytes, int64_t* stats,
+                   cudaStream_t stream);
+int ep_exec_gru_level(const int64_t* desc, const int64_t* globals, const float* pts, int64_t u, float vres,
+                      const float* h, int ld_h, const float* x, int ld_x, float* out, int ld_out, void* arena,
+                      size_t arena_bytes, int64_t* stats, cudaStream_t stream);
+int ep_exec_linear4x(const int64_t* desc, const float* x, int ld_x, int64_t m, const int64_t* outs, void* arena,
+                     size_t arena_bytes, int64_t* stats, cudaStream_t stream);
+int ep_exec_init_head(const int64_t* desc, const int64_t* globals, const float* var, int ld_var, const int32_t* coords,
+                      int64_t m, int sx, int sy, int sz, float* occ, void* arena, size_t arena_bytes, int64_t* stats,
+                      cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

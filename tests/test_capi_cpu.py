@@ -60,3 +60,43 @@ def test_oracle_is_not_imported_by_the_product():
         if fn.endswith(".py"):
             src = open(os.path.join(root, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_replicas_share_parameters_but_not_state():
+    from eprecon_b200 import synth
+    from eprecon_b200.neucon_network import NeuConNet
+    from eprecon_b200.streams import replicate
+    net = NeuConNet(synth.make_cfg())
+    synth.fill_parameters_(net, 1)
+    rep = replicate(net)
+    a, b = dict(net.named_parameters()), dict(rep.named_parameters())
+    assert a.keys() == b.keys()
+    assert all(a[k].data_ptr() == b[k].data_ptr() for k in a)          # same storage, no weight copy
+    assert rep.gru_fusion is not net.gru_fusion and rep.gru_fusion.global_volume is not net.gru_fusion.global_volume
+    assert rep.training == net.training
+
+
+def test_executor_descriptors_parse_natively():
+    """The flat int64 parameter descriptors executor.py builds are parsed by the SAME C++ reader the native executor uses
+    (ep_exec_desc_check, host only): layout, end markers and the channel bookkeeping must agree for every module."""
+    from eprecon_b200 import _lib, executor, synth
+    from eprecon_b200.neucon_network import NeuConNet
+    net = NeuConNet(synth.make_cfg())
+    synth.fill_parameters_(net, 1)
+    L = _lib.lib()
+    for sp in net.sp_convs:
+        arr, keep = executor._build_spvcnn(sp)
+        assert L.ep_exec_desc_check(0, arr.ctypes.data) == arr.size
+    for gv, gi in zip(net.gru_fusion.fusion_nets_voxel, net.gru_fusion.fusion_nets_img):
+        arr, keep = executor._build_gru((gv, gi))
+        assert L.ep_exec_desc_check(1, arr.ctypes.data) == arr.size
+    for i in range(3):
+        arr, keep = executor._build_lin4x((net.tsdf_preds[i], net.occ_preds[i]))
+        assert L.ep_exec_desc_check(2, arr.ctypes.data) == arr.size
+        arr, keep = executor._build_lin4x((net.panoptic_preds[i],))
+        assert L.ep_exec_desc_check(2, arr.ctypes.data) == arr.size
+    arr, keep = executor._build_init(net.initialization)
+    assert L.ep_exec_desc_check(3, arr.ctypes.data) == arr.size
+    bad = arr.copy()
+    bad[-1] = 0                                                        # broken end marker -> rejected
+    assert L.ep_exec_desc_check(3, bad.ctypes.data) < 0
