@@ -447,6 +447,14 @@ def run_ours(args):
             kernel_share[kind] = {"launches_per_fragment": len(evs) // max(K, 1), "ms_per_fragment": tot_ms / K,
                                   "share_of_single_stream_step": tot_ms / prof_ms if prof_ms else None}
         per_step = len(work.get("spconv_work", []))
+        dump = os.environ.get("EPRECON_BENCH_DUMP")
+        if dump and per_step and len(prof.get("spconv", [])) == per_step * K:
+            # per-launch view of the sparse-conv family: algorithmic work next to the mean CUDA-event duration
+            evs = prof["spconv"]
+            with open(dump, "w") as f:
+                for j, w in enumerate(work["spconv_work"]):
+                    us = 1e3 * sum(evs[k * per_step + j][0].elapsed_time(evs[k * per_step + j][1]) for k in range(K)) / K
+                    f.write(json.dumps(dict(w, us=round(us, 2), impl="ffma" if w["K"] == 1 else ops.SPCONV_IMPL)) + "\n")
         flops = sum(2.0 * w["cin"] * w["cout"] * w["pairs"] for w in work.get("spconv_work", []))
         sp_bytes = sum(4.0 * (w["m_in"] * w["cin"] + w["m_out"] * w["cout"] + w["K"] * w["cin"] * w["cout"] + w["pairs"])
                        for w in work.get("spconv_work", []))

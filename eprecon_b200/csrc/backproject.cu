@@ -607,7 +607,7 @@ int ep_backproject_fused(const int32_t* coords, int64_t n, const float* origin, 
 #define EP_BP_FUSED(CC, MM)                                                                                           \
   do {                                                                                                                \
     if (smem > 48 * 1024 &&                                                                                           \
-        cudaFuncSetAttribute(bp_fused_kernel<CC, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=      \
+        cudaFuncSetAttribute(bp_fused_kernel<CC, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) !=   \
             cudaSuccess)                                                                                              \
       return EP_ERR_CUDA;                                                                                             \
     bp_fused_kernel<CC, MM><<<ntiles, FT, smem, stream>>>((const int4*)coords, (int)n, origin, voxel_size, krcam,     \

@@ -105,7 +105,7 @@ int ep_init_prune(const uint8_t* fine, int bs, int coarse_dim, int out_scale, in
   if (bs < 1 || coarse_dim < 1) return EP_ERR_ARG;
   const size_t smem = 2 * (size_t)coarse_dim * coarse_dim * coarse_dim;
   if (smem > 200 * 1024) return EP_ERR_UNSUPPORTED;
-  if (cudaFuncSetAttribute(init_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  if (cudaFuncSetAttribute(init_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
     return EP_ERR_CUDA;
   init_prune_kernel<<<1, 1024, smem, stream>>>(fine, bs, coarse_dim, out_scale, (int4*)out_coords, out_count);
   EP_CHECK_LAUNCH();

@@ -146,15 +146,20 @@ def _params_of(obj):
 
 
 def _desc(owner, key, obj, build):
-    """Descriptor of `obj` (a module or a tuple of modules), cached on `owner` and rebuilt when any parameter tensor
-    was replaced or modified in place."""
-    tag = tuple((p.data_ptr(), p._version) for p in _params_of(obj))
+    """Descriptor of `obj` (a module or a tuple of modules), cached on `owner` and rebuilt when a parameter tensor was
+    moved (.to / .cuda) or modified in place (load_state_dict, optimizer step).  The Parameter objects themselves are
+    looked up once: walking nn.Module trees on every call cost 3 ms per fragment."""
     cache = owner.__dict__.setdefault("_exec_desc", {})
     hit = cache.get(key)
-    if hit is None or hit[0] != tag:
-        arr, keep = build(obj)
-        hit = cache[key] = (tag, arr, keep, arr.ctypes.data)
-    return hit[3]
+    if hit is not None:
+        tag = tuple((p.data_ptr(), p._version) for p in hit[0])
+        if tag == hit[1]:
+            return hit[4]
+    plist = list(_params_of(obj))
+    tag = tuple((p.data_ptr(), p._version) for p in plist)
+    arr, keep = build(obj)
+    cache[key] = (plist, tag, arr, keep, arr.ctypes.data)
+    return arr.ctypes.data
 
 
 _GLOBALS = {}

@@ -107,30 +107,40 @@ class GRUFusion(nn.Module):
         return out_coords, row_a, row_b, valid
 
     def _fuse_targets(self, inputs, i, scale, rel, dims, updated_xyz):
-        """Reference GT fusion (gru_fusion.py:98-112,205-215,324-327) on a dense 1-channel volume."""
+        """Reference GT fusion (gru_fusion.py:98-112,205-215,324-327) on a dense 1-channel volume.  Same result as the
+        reference's nonzero / boolean-index formulation, written with masked dense ops so that the only host round-trips
+        are the two data-dependent list sizes of the updated sparse GT map (one when the scene has no GT state yet)."""
         lvl = self.cfg.N_LAYER - scale - 1
         occ_t = inputs["occ_list"][lvl][i]
-        tsdf_t = inputs["tsdf_list"][lvl][i][occ_t]
-        coords_t = torch.nonzero(occ_t)
+        tsdf_full = inputs["tsdf_list"][lvl][i]
         tgt = self.target_tsdf_volume[scale]
         dev = occ_t.device
-        dim = self._const(tuple(dims), dev, torch.int64)
         relt = self._const(tuple(rel), dev, torch.int64)
-        gc = tgt["C"] - relt
-        valid_t = ((gc < dim) & (gc >= 0)).all(dim=-1)
-        cc = torch.cat([gc[valid_t], coords_t])[:, :3]
-        tv = torch.cat([tgt["F"][valid_t], tsdf_t.unsqueeze(-1)])
-        vol = torch.full((dims[0], dims[1], dims[2], 1), 1.0, dtype=tv.dtype, device=dev)
-        if cc.shape[0] > 0:
-            vol[cc[:, 0], cc[:, 1], cc[:, 2]] = tv
+        nvol = dims[0] * dims[1] * dims[2]
+        flat = torch.full((nvol + 1,), 1.0, dtype=tgt["F"].dtype, device=dev)     # +1: dump slot for out-of-volume rows
+        ng = tgt["C"].shape[0]
+        valid_t = None
+        if ng > 0:
+            dim = self._const(tuple(dims), dev, torch.int64)
+            gc = tgt["C"] - relt
+            valid_t = ((gc < dim) & (gc >= 0)).all(dim=-1)
+            lin = (gc[:, 0] * dims[1] + gc[:, 1]) * dims[2] + gc[:, 2]
+            flat[torch.where(valid_t, lin, torch.full_like(lin, nvol))] = tgt["F"][:, 0]
+        vol = flat[:nvol].view(dims[0], dims[1], dims[2])
+        vol = torch.where(occ_t, tsdf_full.to(vol.dtype), vol)                    # the current fragment's GT wins
         u = updated_xyz.long()
-        tsdf_target = vol[u[:, 0], u[:, 1], u[:, 2]]
+        tsdf_target = vol[u[:, 0], u[:, 1], u[:, 2]].unsqueeze(-1)
         occ_target = tsdf_target.abs() < 1
-        # update the GT map
-        v = vol.squeeze(-1)
-        keep = v.abs() < 1
-        tgt["F"] = torch.cat([tgt["F"][valid_t == False], v[keep].unsqueeze(-1)])  # noqa: E712
-        tgt["C"] = torch.cat([tgt["C"][valid_t == False], torch.nonzero(keep) + relt])  # noqa: E712
+        # update the GT map: drop the in-volume rows, append every |tsdf| < 1 voxel of the fused local volume
+        keep = torch.nonzero(vol.abs() < 1)
+        new_f = vol[keep[:, 0], keep[:, 1], keep[:, 2]].unsqueeze(-1)
+        new_c = keep + relt
+        if ng > 0:
+            stay = torch.nonzero(valid_t == False).squeeze(1)  # noqa: E712
+            tgt["F"] = torch.cat([tgt["F"][stay], new_f])
+            tgt["C"] = torch.cat([tgt["C"][stay], new_c])
+        else:
+            tgt["F"], tgt["C"] = new_f, new_c
         return tsdf_target, occ_target
 
     def save_mesh(self, scale, outputs, scene):
@@ -221,8 +231,12 @@ class GRUFusion(nn.Module):
             relt = self._const(tuple(rel), dev, torch.int32)
             vpad = values if values.shape[1] == g["F"].shape[1] else torch.nn.functional.pad(
                 values, (0, g["F"].shape[1] - values.shape[1]))
-            g["F"] = torch.cat([g["F"][valid == False], vpad])  # noqa: E712
-            g["C"] = torch.cat([g["C"][valid == False], upd[:, 1:] + relt])  # noqa: E712
+            if g["C"].shape[0] > 0:
+                stay = torch.nonzero(valid == False).squeeze(1)  # noqa: E712  (one size read-back for both gathers)
+                g["F"] = torch.cat([g["F"][stay], vpad])
+                g["C"] = torch.cat([g["C"][stay], upd[:, 1:] + relt])
+            else:
+                g["F"], g["C"] = vpad, upd[:, 1:] + relt
             out_c = upd.clone()
             out_c[:, 1:] *= interval
             coords_all.append(out_c)
