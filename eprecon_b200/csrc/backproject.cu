@@ -84,8 +84,13 @@ bp_count_kernel(const int4* __restrict__ coords, int n, const float* __restrict_
   if (threadIdx.x == 0) block_count[blockIdx.x] = total;
   if (bs == 1) {
     if (threadIdx.x == 0 && total) atomicAdd(valid_per_batch, total);
-  } else if (keep) {
-    atomicAdd(valid_per_batch + b, 1);
+  } else {
+    // batched fragments: one atomic per (warp, batch entry) instead of one per surviving voxel
+    const unsigned act = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const unsigned peers = __match_any_sync(act, b);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(valid_per_batch + b, __popc(peers));
+    }
   }
 }
 
@@ -441,7 +446,13 @@ bp_fused_kernel(const int4* __restrict__ coords, int n, const float* __restrict_
       if (bs == 1 && total) atomicAdd(totals, total);
     }
   }
-  if (bs > 1 && keep) atomicAdd(totals + c.x, 1);
+  if (bs > 1 && t < TV) {   // warps 0-1 hold the tile's voxels: one atomic per (warp, batch entry), not one per voxel
+    const unsigned act = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const unsigned peers = __match_any_sync(act, c.x);
+      if ((t & 31) == __ffs(peers) - 1) atomicAdd(totals + c.x, __popc(peers));
+    }
+  }
   if (keep) s_list[rank] = t;
   __syncthreads();
   const int base = s_base;

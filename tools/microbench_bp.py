@@ -116,5 +116,22 @@ def main(iters=20):
                           "GBs_gather_only": round((4 * V * C * H * W + (20 + 4 * C) * m) / t[3] / 1e6, 1)}))
 
 
+def batched(B):
+    """One launch over B fragments' level-2 candidates (operands >> L2): the HBM-bound view (same probe as bench.py)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    inputs, _, _ = synth.make_fragment(seed=1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    print(json.dumps(bench.bp_batched_probe(torch.device("cuda", 0), inputs, peaks, B=B)))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--batched":
+        for b in sys.argv[2].split(","):
+            batched(int(b))
+    else:
+        main()
