@@ -10,8 +10,10 @@ coarse-to-fine loop keeps int32 coordinates on the device end to end and replace
 Host syncs per level: survivor count of the back-projection, voxel counts of the voxelisations, union size,
 occupied count (each a 4-byte read the reference also performs).
 
-Not built this round (SURVEY.md section 8 f): the panoptic branch (:516-622) — `outputs['panoptic_info']` is None —
-and the training losses (`loss_dict` holds zeros under the reference's keys).
+The panoptic branch (:516-590; SURVEY.md section 8 f row 1) runs when `with_panoptic` is set (or `cfg.PANOPTIC`):
+level alignment -> per-level panoptic MLPs -> SubM mask features -> eprecon_b200.mask3dformer decoder -> panoptic_post,
+and `outputs['panoptic_info']` holds the reference's per-fragment list; it is None otherwise (BASELINE configs[1] is the
+TSDF path).  Not built: the training losses (`loss_dict` holds zeros under the reference's keys).
 """
 import numpy as np
 import torch
@@ -25,6 +27,7 @@ except Exception:  # pragma: no cover
 
 from . import _lib, executor, ops
 from .gru_fusion import GRUFusion
+from .mask3dformer import MultiScaleMaskedTransformerDecoder, panoptic_post
 from .modules import SPVCNN, Linear4xTrans, Panoptic_Feat_Fusion
 from .occupancy_initialization import Back_Project, Occupancy_Initialization
 from .tensor import PointTensor
@@ -60,9 +63,16 @@ class NeuConNet(nn.Module):
         self.panoptic_preds = nn.ModuleList()
         self.initialization = Occupancy_Initialization(ch_initialization, ch_initialization_down, n_views)
         self.panoptic_feat_fusion = Panoptic_Feat_Fusion(channels[2], panoptic_channels, ch_initialization)
-        # First stage of the panoptic branch (neucon_network.py:516-560): level alignment, per-level panoptic MLPs and the
-        # submanifold mask features.  Off by default: BASELINE configs[1] is the TSDF path; the decoder itself is not built yet.
+        # panoptic decoder, same hyper-parameters as neucon_network.py:59-71
+        self.dec_layers = 6
+        self.panoptic = MultiScaleMaskedTransformerDecoder(mask_classification=True, num_classes=20, hidden_dim=panoptic_channels,
+                                                           num_queries=80, nheads=8, dim_feedforward=4 * panoptic_channels,
+                                                           dec_layers=self.dec_layers, pre_norm=False, mask_dim=panoptic_channels)
+        # Panoptic branch (neucon_network.py:516-590).  `with_panoptic_features`: level alignment, per-level panoptic MLPs and
+        # the submanifold mask features only; `with_panoptic`: + decoder + post-processing -> outputs['panoptic_info'].
+        # Off by default: BASELINE configs[1] (the benchmarked workload) is the TSDF path.
         self.with_panoptic_features = False
+        self.with_panoptic = bool(getattr(cfg, "PANOPTIC", False))
         for i in range(len(cfg.THRESHOLDS)):
             self.back_projection.append(Back_Project(ch_initialization[i], materialize_grid=False))
             self.sp_convs.append(SPVCNN(num_classes=1, in_channels=ch_in[i], pres=1, cr=1 / 2 ** i,
@@ -250,7 +260,7 @@ class NeuConNet(nn.Module):
             pre_tsdf = ops.gather_rows(tsdf_c, 1, index=index)
             pre_feat[:, cv] = pre_tsdf[:, 0]
             pre_feat[:, cv + 1] = ops.gather_rows(occ_c, 1, index=index)[:, 0]
-            if self.with_panoptic_features:
+            if self.with_panoptic_features or self.with_panoptic:
                 pano_feats.append(ops.gather_rows(feat_all, cv + c_img, index=index))
                 pano_coords.append(pre_coords)
             self.last_sizes[f"level{i}"] = {"candidates": int(res["count"].shape[0]), "projected": m, "fused": u,
@@ -259,9 +269,26 @@ class NeuConNet(nn.Module):
                 outputs["coords"] = pre_coords.long()
                 outputs["tsdf"] = pre_tsdf[:, :1]
         outputs["panoptic_info"] = None
-        if self.with_panoptic_features:
+        if self.with_panoptic_features or self.with_panoptic:
             outputs["panoptic_features"] = self.panoptic_prepare(pano_coords, pano_feats, bs)
+            if self.with_panoptic:
+                outputs["panoptic_outs"], outputs["panoptic_info"] = self.panoptic_decode(outputs["panoptic_features"], bs)
         return outputs, loss_dict
+
+    @torch.no_grad()
+    def panoptic_decode(self, pf, bs):
+        """models/neucon_network.py:560-586: per fragment, decoder over the three aligned levels + panoptic_post."""
+        shape = tuple(int(n) for n in self.cfg.N_VOX)
+        outs, infos = [], []
+        for b in range(bs):
+            sel = [slice(None) if bs == 1 else torch.nonzero(pf["coords"][p][:, 0] == b).squeeze(1) for p in range(3)]
+            feats = [pf["feats"][p][sel[p]][:, :48].unsqueeze(0).permute(0, 2, 1) for p in range(3)]
+            coords = [pf["coords"][p][sel[p]][:, 1:].unsqueeze(0) for p in range(3)]
+            mask = pf["mask_features"][sel[2]][:, :48].unsqueeze(0).permute(0, 2, 1)
+            out = self.panoptic(panoptic_features=feats, panoptic_coords=coords, mask_features=mask, spitial_shape=shape)
+            outs.append(out)
+            infos.append(panoptic_post(out))
+        return outs, infos
 
     @torch.no_grad()
     def panoptic_prepare(self, coords, feats, bs):

@@ -31,6 +31,7 @@ def replicate(net):
         b.data = src_b[name].data
     rep.train(net.training)
     rep.with_panoptic_features = net.with_panoptic_features
+    rep.with_panoptic = net.with_panoptic
     return rep
 
 

@@ -183,11 +183,17 @@ def _fill_one(name, p, seed):
     return v.to(p.dtype)
 
 
-def fill_parameters_(module, seed=1):
-    """Overwrite every parameter of `module` with values that depend only on (name, shape, seed)."""
+def fill_parameters_(module, seed=1, prefix=""):
+    """Overwrite every parameter of `module` with values that depend only on (prefix + name, shape, seed).  The one
+    random BUFFER of the path (the Fourier matrix `gauss_B` of the panoptic decoder's positional encoding,
+    models/voxel_position_encoding.py:66-70) is filled the same way, as a unit normal."""
     with torch.no_grad():
         for name, p in sorted(module.named_parameters(), key=lambda kv: kv[0]):
-            p.copy_(_fill_one(name, p, seed))
+            p.copy_(_fill_one(prefix + name, p, seed))
+        for name, b in sorted(module.named_buffers(), key=lambda kv: kv[0]):
+            if name.endswith("gauss_B"):
+                g = torch.Generator().manual_seed((seed * 2654435761 + zlib.crc32((prefix + name).encode())) % (2 ** 63 - 1))
+                b.copy_(torch.randn(tuple(b.shape), generator=g).to(b.dtype))
     return module
 
 

@@ -535,3 +535,125 @@ def panoptic_prepare(sd, cfg, trace, chunk=2048):
     for k in range(3):
         x = _subm_residual(sd, f"panoptic_feat_fusion.mask_feat_extraction_{k}", x, cz, shape)
     return {"coords": coords, "feats": pf, "mask_features": x}
+
+
+# ======================================================================= panoptic decoder (next row)
+# The decoder is plain ATen in the reference (models/mask3dformer.py, models/voxel_position_encoding.py): this
+# restatement is pinned DIRECTLY against the unmodified reference modules (tests/golden/mask3dformer_small.npz).
+N_HEADS = 8
+
+
+def fourier_positions(sd, p, xyz, shape):
+    """PositionEmbeddingCoordsSine.get_fourier_embeddings with normalize=True (models/voxel_position_encoding.py:116-146;
+    called from mask3dformer.py:318-335 with input_range = [0, spatial shape]): xyz int [N,3] -> [N, d_pos]."""
+    x = xyz.float()
+    src_diff = torch.tensor([float(s) for s in shape], dtype=torch.float32)
+    x = ((x - 0.0) * 1.0) / src_diff + 0.0        # shift_scale_points (:11-40) with dst range [0, 1]
+    x = x * f32(2 * np.pi)
+    proj = x @ sd[p + ".gauss_B"]
+    return torch.cat([proj.sin(), proj.cos()], 1)
+
+
+def _mha(sd, p, query, key, value, blocked=None, nheads=N_HEADS):
+    """nn.MultiheadAttention forward (batch of one, no dropout): query [Q,E], key/value [N,E]; blocked bool [Q,N]
+    (True = may not attend, the same for every head, mask3dformer.py:444)."""
+    E = query.shape[1]
+    W, b = sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"]
+    q = F.linear(query, W[:E], b[:E])
+    k = F.linear(key, W[E:2 * E], b[E:2 * E])
+    v = F.linear(value, W[2 * E:], b[2 * E:])
+    hd = E // nheads
+    q = q.view(-1, nheads, hd).transpose(0, 1)           # [h,Q,hd]
+    k = k.view(-1, nheads, hd).transpose(0, 1)
+    v = v.view(-1, nheads, hd).transpose(0, 1)
+    s = (q @ k.transpose(1, 2)) / float(np.sqrt(hd))
+    if blocked is not None:
+        s = s.masked_fill(blocked.unsqueeze(0), float("-inf"))
+    a = torch.softmax(s, dim=-1)
+    o = (a @ v).transpose(0, 1).reshape(-1, E)
+    return F.linear(o, sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
+
+
+def nearest_fine_index(coarse_xyz, fine_xyz, chunk=64):
+    """mask3dformer.py:361-368: `argmin(cdist(fine, coarse[None]), dim=1)` reduces over the FINE axis, i.e. for every
+    coarse voxel the index of its nearest level-2 voxel (first index on ties; distances between integer voxels are
+    exact in fp32, so ties are exact).  Brute force with integer distances."""
+    fine = fine_xyz.to(torch.int64)
+    out = torch.empty(len(coarse_xyz), dtype=torch.int64)
+    big = int(len(fine)) + 1
+    for s0 in range(0, len(coarse_xyz), chunk):
+        c = coarse_xyz[s0:s0 + chunk].to(torch.int64)
+        d2 = ((fine.unsqueeze(0) - c.unsqueeze(1)) ** 2).sum(-1)          # [chunk, N2]
+        key = d2 * big + torch.arange(len(fine)).unsqueeze(0)
+        out[s0:s0 + chunk] = key.min(dim=1).values % big
+    return out
+
+
+def _pred_heads(sd, p, output, mask_features, index):
+    """forward_prediction_heads (mask3dformer.py:431-447); index None = level 2 (all voxels, :370)."""
+    d = _ln(output, sd, p + ".decoder_norm")
+    logits = _lin(d, sd, p + ".class_embed")
+    e = F.relu(_lin(d, sd, p + ".mask_embed.layers.0"))
+    e = F.relu(_lin(e, sd, p + ".mask_embed.layers.1"))
+    e = _lin(e, sd, p + ".mask_embed.layers.2")
+    masks = e @ mask_features.t()                                          # [Q, N2]
+    sel = masks if index is None else masks[:, index]
+    blocked = torch.sigmoid(sel) < 0.5
+    return logits, masks, blocked
+
+
+def mask3dformer(sd, p, feats, coords_xyz, mask_features, shape, n_layers=6):
+    """MultiScaleMaskedTransformerDecoder.forward (mask3dformer.py:338-429), one fragment.
+    feats[l] [N_l,48] (level-aligned panoptic features), coords_xyz[l] int [N_l,3], mask_features [N_2,48]."""
+    pos = [fourier_positions(sd, p + ".pos_enc", coords_xyz[l], shape) for l in range(3)]
+    src = [feats[l] + sd[p + ".level_embed.weight"][l].unsqueeze(0) for l in range(3)]
+    index = [nearest_fine_index(coords_xyz[0], coords_xyz[2]), nearest_fine_index(coords_xyz[1], coords_xyz[2]), None]
+    qpos = sd[p + ".query_embed.weight"]
+    out = sd[p + ".query_feat.weight"]
+    logits, masks, blocked = _pred_heads(sd, p, out, mask_features, index[0])
+    aux = [(logits, masks)]
+    for j in range(n_layers):
+        l = j % 3
+        blocked = blocked & ~blocked.all(dim=1, keepdim=True)             # a fully blocked query attends everywhere (:389)
+        t2 = _mha(sd, f"{p}.transformer_cross_attention_layers.{j}.multihead_attn", out + qpos, src[l] + pos[l], src[l], blocked)
+        out = _ln(out + t2, sd, f"{p}.transformer_cross_attention_layers.{j}.norm")
+        t2 = _mha(sd, f"{p}.transformer_self_attention_layers.{j}.self_attn", out + qpos, out + qpos, out)
+        out = _ln(out + t2, sd, f"{p}.transformer_self_attention_layers.{j}.norm")
+        ff = f"{p}.transformer_ffn_layers.{j}"
+        t2 = _lin(F.relu(_lin(out, sd, ff + ".linear1")), sd, ff + ".linear2")
+        out = _ln(out + t2, sd, ff + ".norm")
+        logits, masks, blocked = _pred_heads(sd, p, out, mask_features, index[(j + 1) % 3])
+        aux.append((logits, masks))
+    return {"pred_logits": logits, "pred_masks": masks, "aux": aux[:-1], "index": index[:2]}
+
+
+def panoptic_inference(mask_cls, mask_pred, object_mask_threshold=0.3, thing_id=tuple(range(3, 21)), overlap_threshold=0.5):
+    """mask3dformer.py:516-581: mask_cls [Q, classes+1], mask_pred [Q, N] logits -> (panoptic_seg int32 [N], segments)."""
+    scores, labels = torch.softmax(mask_cls, -1).max(-1)
+    prob = torch.sigmoid(mask_pred)
+    keep = (labels != 0) & (scores > object_mask_threshold)
+    seg = torch.zeros(mask_pred.shape[-1], dtype=torch.int32)
+    info = []
+    if int(keep.sum()) == 0:
+        return seg, info
+    ks, kc, km = scores[keep], labels[keep], prob[keep]
+    winner = (ks.view(-1, 1) * km).argmax(0)
+    next_id, stuff = 0, {}
+    for k in range(len(kc)):
+        cls = int(kc[k])
+        thing = cls in thing_id
+        area = int((winner == k).sum())
+        orig = int((km[k] >= 0.5).sum())
+        m = (winner == k) & (km[k] >= 0.5)
+        if area > 0 and orig > 0 and int(m.sum()) > 0:
+            if area / orig < overlap_threshold:
+                continue
+            if not thing:
+                if cls in stuff:
+                    seg[m] = stuff[cls]
+                    continue
+                stuff[cls] = next_id + 1
+            next_id += 1
+            seg[m] = next_id
+            info.append({"id": next_id, "isthing": bool(thing), "category_id": cls})
+    return seg, info

@@ -1,0 +1,130 @@
+"""Panoptic decoder on CUDA vs the reference fixture (tests/golden/mask3dformer_small.npz, outputs of
+the UNMODIFIED models/mask3dformer.py) and vs the CPU oracle at the small golden NeuConNet configuration."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from eprecon_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-3
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "mask3dformer_small.npz")
+GOLD_NET = os.path.join(HERE, "golden", "neucon_small.npz")
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).detach().cpu().float(), torch.as_tensor(b).detach().cpu().float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def c4(xyz):
+    return torch.cat([torch.zeros_like(xyz[:, :1]), xyz], 1).to(torch.int32).contiguous().cuda()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def decoder(cuda_lib):
+    from eprecon_b200.mask3dformer import MultiScaleMaskedTransformerDecoder
+    dec = MultiScaleMaskedTransformerDecoder(mask_classification=True, num_classes=20, hidden_dim=48, num_queries=80, nheads=8,
+                                             dim_feedforward=192, dec_layers=6, pre_norm=False, mask_dim=48)
+    synth.fill_parameters_(dec, 1, prefix="panoptic.")
+    return dec.cuda()
+
+
+def test_nearest_fine_index_hash_join(cuda_lib, gold):
+    from oracle import restate
+    from eprecon_b200.mask3dformer import nearest_fine_index
+    coords = [torch.from_numpy(gold[f"coords{l}"].astype(np.int64)) for l in range(3)]
+    i0 = nearest_fine_index(c4(coords[0]), c4(coords[2]), 5)
+    i1 = nearest_fine_index(c4(coords[1]), c4(coords[2]), 1)
+    assert np.array_equal(i0.cpu().numpy(), gold["index0"])        # the reference's cdist + argmin, bit-exact
+    assert np.array_equal(i1.cpu().numpy(), gold["index1"])
+    # random sparse set with many equidistant candidates: first-row tie rule
+    g = torch.Generator().manual_seed(5)
+    fine = torch.unique(torch.randint(0, 40, (6000, 3), generator=g), dim=0)
+    fine = fine[torch.randperm(len(fine), generator=g)]
+    for step, radius in ((2, 1), (4, 5)):
+        coarse = torch.unique(torch.floor_divide(fine, step) * step, dim=0)
+        coarse = coarse[torch.randperm(len(coarse), generator=g)]
+        want = restate.nearest_fine_index(coarse, fine)
+        got = nearest_fine_index(c4(coarse), c4(fine), radius)
+        assert torch.equal(got.cpu(), want), step
+
+
+def test_decoder_matches_reference_fixture(decoder, gold):
+    coords = [torch.from_numpy(gold[f"coords{l}"].astype(np.int64)).cuda() for l in range(3)]
+    feats = [torch.from_numpy(gold[f"feats{l}"]).cuda() for l in range(3)]
+    mf = torch.from_numpy(gold["mask_features"]).cuda()
+    dim = int(gold["dim"])
+    out = decoder([f.unsqueeze(0).permute(0, 2, 1) for f in feats], [c.unsqueeze(0) for c in coords],
+                  mf.unsqueeze(0).permute(0, 2, 1), (dim, dim, dim))
+    assert rel(out["pred_logits"][0], gold["pred_logits"]) < RTOL
+    assert rel(out["pred_masks"][0], gold["pred_masks"]) < RTOL
+    assert len(out["aux_outputs"]) == 6
+    for j, a in enumerate(out["aux_outputs"]):
+        assert rel(a["pred_logits"][0], gold["aux_logits"][j]) < RTOL, j
+    from eprecon_b200.mask3dformer import panoptic_post
+    seg, info = panoptic_post(out)["panoptic_seg"]
+    assert seg.dtype == torch.int32 and (seg.cpu().numpy() != gold["post_seg"]).mean() <= 1e-3
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_panoptic_inference_matches_reference(cuda_lib, gold, case):
+    from eprecon_b200.mask3dformer import panoptic_inference
+    seg, info = panoptic_inference(torch.from_numpy(gold[f"pi{case}_cls"]).cuda(), torch.from_numpy(gold[f"pi{case}_msk"]).cuda())
+    assert np.array_equal(seg.cpu().numpy(), gold[f"pi{case}_seg"])
+    got = np.asarray([[d["id"], int(d["isthing"]), d["category_id"]] for d in info], dtype=np.int32).reshape(-1, 3)
+    assert np.array_equal(got, gold[f"pi{case}_info"])
+
+
+def test_decoder_rejects_cpu_tensors():
+    from eprecon_b200._lib import EpreconError
+    from eprecon_b200.mask3dformer import MultiScaleMaskedTransformerDecoder
+    dec = MultiScaleMaskedTransformerDecoder(mask_classification=True, num_classes=20, hidden_dim=48, num_queries=80, nheads=8,
+                                             dim_feedforward=192, dec_layers=1, pre_norm=False, mask_dim=48)
+    x = torch.zeros(1, 48, 10)
+    with pytest.raises(EpreconError):
+        dec([x, x, x], [torch.zeros(1, 10, 3, dtype=torch.long)] * 3, x, (8, 8, 8))
+
+
+def test_neucon_forward_with_panoptic_head(cuda_lib):
+    """NeuConNet.forward with the full panoptic head on the small golden configuration: the decoder runs on the product's
+    own level-aligned features (checked against the oracle in test_neucon_gpu.py) and must agree with the oracle decoder
+    fed the same features."""
+    from oracle import restate
+    from eprecon_b200.neucon_network import NeuConNet
+    g = np.load(GOLD_NET)
+    n_vox = tuple(int(v) for v in g["n_vox"])
+    cfg = synth.make_cfg(n_vox=n_vox)
+    cfg.THRESHOLDS = [float(v) for v in g["thresholds"]]
+    net = NeuConNet(cfg)
+    sd = synth.synthetic_state_dict(net, 1)
+    net = net.cuda()
+    net.with_panoptic = True
+    inputs, fa, fb = synth.make_fragment(seed=int(g["seed"]), n_views=int(g["n_views"]),
+                                         image_hw=tuple(int(v) for v in g["image_hw"]), n_vox=n_vox)
+    cin = {k: (v.cuda() if torch.is_tensor(v) else ([t.cuda() for t in v] if isinstance(v, list) and torch.is_tensor(v[0]) else v))
+           for k, v in inputs.items()}
+    cin["scene"] = ["scene_pano_full"]
+    out, _ = net([[t.cuda() for t in f] for f in fa], [[t.cuda() for t in f] for f in fb], cin, {})
+    assert "coords" in out and isinstance(out["panoptic_info"], list) and len(out["panoptic_info"]) == 1
+    seg, info = out["panoptic_info"][0]["panoptic_seg"]
+    pf = out["panoptic_features"]
+    assert seg.shape[0] == pf["coords"][2].shape[0] == out["coords"].shape[0]
+    feats = [pf["feats"][p][:, :48].cpu() for p in range(3)]
+    xyz = [pf["coords"][p][:, 1:].cpu() for p in range(3)]
+    with torch.no_grad():
+        want = restate.mask3dformer(sd, "panoptic", feats, xyz, pf["mask_features"][:, :48].cpu(), n_vox)
+    got = out["panoptic_outs"][0]
+    assert rel(got["pred_logits"][0], want["pred_logits"]) < RTOL
+    assert rel(got["pred_masks"][0], want["pred_masks"]) < RTOL
+    wseg, winfo = restate.panoptic_inference(want["pred_logits"], want["pred_masks"])
+    assert (seg.cpu() != wseg).float().mean().item() <= 1e-3
+    assert [d["category_id"] for d in info] == [d["category_id"] for d in winfo]
