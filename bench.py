@@ -33,7 +33,7 @@ FULL_OVER_SAMPLE = 31.0
 FULL_NOTE = ("value / 31: the oracle's full 3-level fragment took 130 s vs 4.2 s for this sample on the 8-core build container; "
              "level 2 (210 k candidate voxels) is skipped in the timed sample to keep the run within minutes")
 METRIC = "fragments/sec (9x640x480, 3-level 96^3)"
-DEFAULT_STREAMS = 4   # fragments in flight per GPU (EPRECON_STREAMS overrides)
+DEFAULT_STREAMS = 8   # fragments in flight per GPU (EPRECON_STREAMS overrides); 1/4/8 streams measured 44/70/81 fragments/s
 # dram__bytes_read.sum + dram__bytes_write.sum of one level-2 spconv_tc_kernel<3> launch (ncu --set full)
 SPCONV_TRAFFIC = {"bytes": 41.3e6, "note": "dram read+write bytes of one level-2 launch (74->8 ch, 200k rows) from "
                                            "profiles/r01_spconv_tc_v2_ncu_summary.csv"}
@@ -463,9 +463,13 @@ def run_ours(args):
         single = {"ms_per_fragment": single_ms, "fragments_per_s": 1e3 / single_ms,
                   "note": "one fragment at a time on one stream (latency view of the same step)"}
         # launch count of one fragment on the shipped (native-executor) path
+        # launch count of one steady-state fragment; cudaProfilerStart/Stop bracket exactly this fragment, so that
+        # `ncu --profile-from-start off ... python bench.py` lists one fragment of this very command (profiles/README.md)
         _lib.LAUNCHES["n"] = 0
+        torch.cuda.profiler.start()
         fragment(net0, resident[0], "count")
         torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         launches_per_fragment = _lib.LAUNCHES["n"]
         # per-launch events need the per-kernel Python programs (the native executor issues the very same launches
         # from C++, where bench.py cannot bracket them): same kernels, same arguments, same order

@@ -357,7 +357,7 @@ constexpr int TV = 64;   // candidate voxels per CTA: 4 threads share a voxel's 
 constexpr unsigned long long TS_AGG = 1ULL << 32, TS_PREFIX = 2ULL << 32;
 
 template <int C, int MODE>
-__global__ void __launch_bounds__(FT)
+__global__ void __launch_bounds__(FT, (C <= 40 ? 5 : 3))
 bp_fused_kernel(const int4* __restrict__ coords, int n, const float* __restrict__ origin, float vs,
                 const float* __restrict__ kr, int V, int bs, int H, int W, const float* __restrict__ feats,
                 int min_views, float* __restrict__ count, int4* __restrict__ out_coords,
@@ -365,13 +365,16 @@ bp_fused_kernel(const int4* __restrict__ coords, int n, const float* __restrict_
                 float* __restrict__ zbar, unsigned long long* __restrict__ tile_state, int* __restrict__ ticket,
                 int* __restrict__ totals /*[bs+1]*/, int ntiles) {
   constexpr int G = C / 4, VPW = 32 / G;
-  extern __shared__ float s_dyn[];           // [V*bs*16] KRt | float2 s_pos[V][TV] | float s_z[V][TV]
+  extern __shared__ __align__(16) float s_dyn[];   // [V*bs*16] KRt | float2 s_pos[V][TV] | float s_z[V][TV] | float4 s_out[TV][C/4]
   float* s_kr = s_dyn;
   float2* s_pos = reinterpret_cast<float2*>(s_dyn + ((V * bs * 16 + 3) & ~3));
   float* s_z = reinterpret_cast<float*>(s_pos + V * TV);
+  float4* s_out = reinterpret_cast<float4*>(s_z + V * TV);   // [TV][C/4] gathered rows of the tile's survivors
+  __shared__ float s_zres[TV];
   __shared__ uint32_t s_mask[TV];
   __shared__ int4 s_coord[TV];
   __shared__ int s_list[TV];
+  __shared__ int s_rank[TV];
   __shared__ int s_scan[33];
   __shared__ int s_tile, s_base;
   const int t = threadIdx.x;
@@ -404,7 +407,8 @@ bp_fused_kernel(const int4* __restrict__ coords, int n, const float* __restrict_
     }
   }
   __syncthreads();
-  // ---- phase B: stable compaction offset (block scan + warp-parallel decoupled look-back)
+  // ---- phase B1: survivors of this tile (block scan); the tile's aggregate is published at once so that later tiles
+  //      never wait on this one's gather
   int keep = 0;
   uint32_t m = 0;
   int4 c = make_int4(0, 0, 0, 0);
@@ -418,33 +422,10 @@ bp_fused_kernel(const int4* __restrict__ coords, int n, const float* __restrict_
   }
   int total;
   const int rank = ep_block_excl_scan(keep, s_scan, &total);
-  if (t < 32) {
+  if (t == 0) {
     volatile unsigned long long* ts = tile_state;
-    if (t == 0) {
-      __threadfence();
-      ts[tile] = (tile == 0 ? TS_PREFIX : TS_AGG) | (unsigned long long)(unsigned)total;
-    }
-    int prefix = 0;
-    int p = tile - 1 - t;
-    bool done = tile == 0;
-    while (!done) {
-      unsigned long long st = TS_PREFIX;            // tiles before 0: an empty prefix
-      if (p >= 0) { do { st = ts[p]; } while ((st >> 32) == 0); }
-      const unsigned has_prefix = __ballot_sync(0xffffffffu, (st >> 32) == 2);
-      const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;
-      int contrib = (t <= first) ? (int)(st & 0xffffffffULL) : 0;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-      prefix += contrib;
-      done = has_prefix != 0;
-      p -= 32;
-    }
-    if (t == 0) {
-      if (tile > 0) { __threadfence(); ts[tile] = TS_PREFIX | (unsigned long long)(unsigned)(prefix + total); }
-      s_base = prefix;
-      if (tile == ntiles - 1) totals[bs] = prefix + total;
-      if (bs == 1 && total) atomicAdd(totals, total);
-    }
+    __threadfence();
+    ts[tile] = (tile == 0 ? TS_PREFIX : TS_AGG) | (unsigned long long)(unsigned)total;
   }
   if (bs > 1 && t < TV) {   // warps 0-1 hold the tile's voxels: one atomic per (warp, batch entry), not one per voxel
     const unsigned act = __ballot_sync(0xffffffffu, keep);
@@ -454,14 +435,12 @@ bp_fused_kernel(const int4* __restrict__ coords, int n, const float* __restrict_
     }
   }
   if (keep) s_list[rank] = t;
+  if (t < TV) s_rank[t] = keep ? rank : -1;
   __syncthreads();
-  const int base = s_base;
-  if (keep) {
-    out_coords[base + rank] = c;
-    out_vis[base + rank] = m;
-    if (out_src) out_src[base + rank] = i;
-  }
-  // ---- phase C: gather (lanes split the channel quads of VPW voxels per warp pass)
+  // ---- phase C: gather into shared memory (lanes split the channel quads of VPW voxels per warp pass).  The output
+  //      row of a survivor needs the tile's global offset, which is looked up AFTER the gather: by then the predecessors
+  //      have published their counts and the look-back returns without spinning (the first version looked back first
+  //      and parked 7 of 8 warps at a barrier: 36 % of all stall samples, profiles/r01_bp_fused_ncu_summary.txt).
   const int lane = t & 31, warp = t >> 5;
   const int sub = lane / G, cq = lane % G;
   const size_t plane = (size_t)H * W * C;
@@ -508,10 +487,53 @@ bp_fused_kernel(const int4* __restrict__ coords, int n, const float* __restrict_
         res = make_float4(__fdiv_rn(var.x, cntf), __fdiv_rn(var.y, cntf), __fdiv_rn(var.z, cntf),
                           __fdiv_rn(var.w, cntf));
       }
-      *reinterpret_cast<float4*>(out + (size_t)(base + k) * ldo + cq * 4) = res;
-      if (zbar && cq == 0) zbar[base + k] = __fdiv_rn(zsum, cntf);
+      s_out[k * G + cq] = res;
+      if (zbar && cq == 0) s_zres[k] = __fdiv_rn(zsum, cntf);
     }
   }
+  // ---- phase B2: global offset of the tile (warp-parallel decoupled look-back over the predecessors' tile states)
+  if (t < 32) {
+    volatile unsigned long long* ts = tile_state;
+    int prefix = 0;
+    int p = tile - 1 - t;
+    bool done = tile == 0;
+    while (!done) {
+      unsigned long long st = TS_PREFIX;            // tiles before 0: an empty prefix
+      if (p >= 0) { do { st = ts[p]; } while ((st >> 32) == 0); }
+      const unsigned has_prefix = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+      const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;
+      int contrib = (t <= first) ? (int)(st & 0xffffffffULL) : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+      prefix += contrib;
+      done = has_prefix != 0;
+      p -= 32;
+    }
+    if (t == 0) {
+      if (tile > 0) { __threadfence(); ts[tile] = TS_PREFIX | (unsigned long long)(unsigned)(prefix + total); }
+      s_base = prefix;
+      if (tile == ntiles - 1) totals[bs] = prefix + total;
+      if (bs == 1 && total) atomicAdd(totals, total);
+    }
+  }
+  __syncthreads();
+  // ---- stores: compacted coords / visibility / source row, then the gathered rows
+  const int base = s_base;
+  if (t < TV) {
+    const int r = s_rank[t];
+    if (r >= 0) {
+      out_coords[base + r] = s_coord[t];
+      out_vis[base + r] = s_mask[t];
+      if (out_src) out_src[base + r] = tile * TV + t;
+    }
+  }
+  // rows base .. base+total-1 are contiguous in `out` (up to the row pitch): all 256 threads copy quads, coalesced
+  for (int e = t; e < total * G; e += FT) {
+    const int k = e / G, q = e - k * G;
+    *reinterpret_cast<float4*>(out + (size_t)(base + k) * ldo + q * 4) = s_out[e];
+  }
+  if (zbar)
+    for (int k = t; k < total; k += FT) zbar[base + k] = s_zres[k];
 }
 
 template <int MODE>
@@ -613,7 +635,7 @@ int ep_backproject_fused(const int32_t* coords, int64_t n, const float* origin, 
   int* ticket = (int*)(tile_state + ntiles);
   cudaMemsetAsync(workspace, 0, (size_t)ntiles * sizeof(unsigned long long) + sizeof(int), stream);
   cudaMemsetAsync(totals, 0, sizeof(int) * (bs + 1), stream);
-  const size_t smem = (size_t)(((n_views * bs * 16 + 3) & ~3) + n_views * TV * 2 + n_views * TV) * sizeof(float);
+  const size_t smem = (size_t)(((n_views * bs * 16 + 3) & ~3) + n_views * TV * 2 + n_views * TV + TV * channels) * sizeof(float);
   if (smem > 160 * 1024) return EP_ERR_UNSUPPORTED;
 #define EP_BP_FUSED(CC, MM)                                                                                           \
   do {                                                                                                                \

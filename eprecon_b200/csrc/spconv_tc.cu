@@ -14,6 +14,8 @@
 // (rel. error 2^-11 per product); PREC == 3 is the error-compensated split  a = a_hi + a_lo, b = b_hi + b_lo,
 // a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo  (dropped term 2^-22), i.e. fp32-grade results at 3 MMAs per slab --
 // this keeps the 1e-3 end-to-end parity budget of the north star through ~40 stacked layers.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -78,22 +80,35 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // stage the tile's neighbour table transposed to [k][row]: one warp per row, lanes over the K offsets (coalesced
-  // global read, conflict-free smem write thanks to the odd stride) and collect the active-offset mask on the way
+  // stage the tile's neighbour table transposed to [k][row].  The tile's slab nbr[row0*K .. (row0+128)*K) is contiguous:
+  // every thread issues PU independent coalesced loads before the first store (the first version walked one row per warp
+  // with a load -> store dependency per iteration and showed up as 19 % of the stall samples of a one-wave launch,
+  // profiles/r01_spconv_tc_v5_ncu_summary.txt) and collects the mask of offsets that have a neighbour in the tile.
   {
-    const int nwarps = blockDim.x >> 5;
-    for (int kq = lane; kq < K; kq += 32) {
-      const bool mine = kq >= kb && kq < ke;
-      int any = 0;
-      for (int r = warp; r < TMR; r += nwarps) {
-        const int j = row0 + r;
-        int v = -1;
-        if (j < m_out) v = nbr ? nbr[(size_t)j * K + kq] : j;
-        s_nbr[kq * NBS + r] = v;
-        any |= (v >= 0);
+    constexpr int NT = TC_THREADS + 32, PU = 6;
+    const int total = TMR * K;
+    const long long base = (long long)row0 * K, lim = (long long)m_out * K;
+    unsigned mine = 0;
+    for (int e0 = 0; e0 < total; e0 += NT * PU) {
+      int v[PU];
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int e = e0 + u * NT + tid;
+        v[u] = -1;
+        if (e < total && base + e < lim) v[u] = nbr ? __ldg(nbr + base + e) : row0 + e;   // no table: K == 1, identity
       }
-      if (any && mine) atomicOr(&s_nk, 1 << kq);
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int e = e0 + u * NT + tid;
+        if (e < total) {
+          const int r = e / K, kq = e - r * K;
+          s_nbr[kq * NBS + r] = v[u];
+          if (v[u] >= 0 && kq >= kb && kq < ke) mine |= 1u << kq;
+        }
+      }
     }
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if (lane == 0 && mine) atomicOr(&s_nk, (int)mine);
   }
   __syncthreads();
   const unsigned kmask = (unsigned)s_nk;   // every thread walks the set bits in ascending order: the active offsets
@@ -353,9 +368,26 @@ extern "C" {
 // rounded up to a multiple of 16, and of 128 when larger than 128).  w_lo is only read when prec == 3.
 // bn_partial: NULL or float[ep_spconv_num_row_tiles(m_out), 2, cout].
 // split-K factor for small problems: spread the K kernel offsets over up to ~one wave of CTAs
+// EPRECON_TC_SPLIT_CTAS=<n> (experiment knob): aim for ~n CTAs per launch instead of one per SM, rounding the factor up
+static int tc_split_target() {
+  static const int target = [] {
+    const char* s = getenv("EPRECON_TC_SPLIT_CTAS");
+    const int v = s ? atoi(s) : 0;
+    return v > 0 ? v : 0;
+  }();
+  return target;
+}
+
 static int tc_splits(int64_t m_out, int npad, int K) {
   const int nt = npad > 128 ? 128 : npad;
   const long long ctas = (long long)ep_div_up(m_out, TMR) * (npad / nt);
+  const int target = tc_split_target();
+  if (target > 0) {
+    if (K < 2 || ctas >= target) return 1;
+    long long s = (target + ctas - 1) / ctas;
+    if (s > K) s = K;
+    return s < 2 ? 1 : (int)s;
+  }
   if (K < 2 || ctas * 2 > EP_NUM_SMS) return 1;
   long long s = EP_NUM_SMS / ctas;
   if (s > K) s = K;
