@@ -43,7 +43,7 @@ using namespace eptc;
 template <int PREC>
 __global__ void __launch_bounds__(TC_THREADS + 32, 3)
 spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*/, const int* __restrict__ nbr, int K,
-                 const float* __restrict__ w_hi, const float* __restrict__ w_lo, int nq /*ceil(cin/4)*/,
+                 const float* __restrict__ w_hi, const float* __restrict__ w_lo, int nq /*4 * ceil(cin/16)*/,
                  int npad /*total padded cout*/, int nt /*columns of this launch's tile*/, int tmem_cols, int cout,
                  const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m_out,
                  float* __restrict__ bn_partial, int bn_rows, int splits, float* __restrict__ partial) {
@@ -124,69 +124,87 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
     const int rowA = tid >> 2, jqA = tid & 3;
     const int nb_items = (KCT / 4) * nt;                         // float4 items of the weight slab
     float4 a_reg[2], bh_reg[2], bl_reg[2];
-    // loop-invariant parts of this thread's two weight-slab items
-    int b_jq[2], b_n[2];
+    // loop-invariant parts of this thread's two weight-slab items: K-chunk of the item and its element offset in a slab
+    unsigned b_rel[2];
     bool b_on[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int e = tid + i * TC_THREADS;
       b_on[i] = e < nb_items;
-      b_jq[i] = b_on[i] ? e / nt : 0;
-      b_n[i] = b_on[i] ? e - b_jq[i] * nt : 0;
+      const int jq = b_on[i] ? e / nt : 0;
+      b_rel[i] = b_on[i] ? (unsigned)(jq * npad + (e - jq * nt)) * 4u : 0u;
+      bh_reg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      bl_reg[i] = bh_reg[i];
     }
-    unsigned ld_rem = kmask;   // offsets still to load (lowest set bit = current one)
-    int ld_c = 0;              // channel slab of the next slab to load
-    auto issue_loads = [&]() {
-      const int k = __ffs(ld_rem) - 1, c = ld_c;
-      const int colq = c * KCT + jqA * 4;
+    const int a_item = jqA * APL + rowA;          // float4 slot of this thread's first A item inside a plane set
+    // load cursor: `rem` = offsets still to load (lowest set bit = current offset k), `c` = channel slab within k.
+    // Everything that only depends on k (the two gathered rows' addresses, the offset's weight block) is computed once
+    // per offset, not once per slab; the weights are addressed with 32-bit element offsets (K*nq*npad*4 < 2^31).
+    unsigned rem = kmask;
+    int c = 0;
+    unsigned w_k = 0;
+    const float* arow[2] = {nullptr, nullptr};
+    auto set_k = [&]() {
+      const int k = __ffs(rem) - 1;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int src = s_nbr[k * NBS + rowA + 64 * i];
-        a_reg[i] = (src >= 0 && colq < cin4) ? __ldg(reinterpret_cast<const float4*>(in + (size_t)src * ld_in + colq))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        arow[i] = src >= 0 ? in + (size_t)src * ld_in + jqA * 4 : nullptr;
       }
-      const size_t wbase = ((size_t)k * nq + (size_t)c * (KCT / 4)) * npad + col0;
+      w_k = (unsigned)(k * nq * npad + col0) * 4u;
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto issue_loads = [&]() {
+      const bool col_ok = c * KCT + jqA * 4 < cin4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        a_reg[i] = (arow[i] && col_ok) ? __ldg(reinterpret_cast<const float4*>(arow[i] + c * KCT)) : zero4;
+      // the weight planes are zero-padded to whole slabs (nq is a multiple of KCT/4): no bounds check, and a 32-bit
+      // unsigned element offset from the (warp-uniform) plane base
+      const unsigned w_s = w_k + (unsigned)(c * (KCT / 4) * npad) * 4u;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        bh_reg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        bl_reg[i] = bh_reg[i];
-        if (b_on[i] && c * (KCT / 4) + b_jq[i] < nq) {
-          const size_t off = (wbase + (size_t)b_jq[i] * npad + b_n[i]) * 4;
-          bh_reg[i] = __ldg(reinterpret_cast<const float4*>(w_hi + off));
-          if (PREC == 3) bl_reg[i] = __ldg(reinterpret_cast<const float4*>(w_lo + off));
+        if (b_on[i]) {
+          bh_reg[i] = __ldg(reinterpret_cast<const float4*>(w_hi + (w_s + b_rel[i])));
+          if (PREC == 3) bl_reg[i] = __ldg(reinterpret_cast<const float4*>(w_lo + (w_s + b_rel[i])));
         }
       }
-      if (++ld_c == nchunk) { ld_c = 0; ld_rem &= ld_rem - 1; }
+      if (++c == nchunk) {
+        c = 0;
+        rem &= rem - 1;
+        if (rem) set_k();
+      }
     };
-    if (T > 0) issue_loads();
+    if (T > 0) { set_k(); issue_loads(); }
+    int stage = 0, round = 0;                      // slab t lives in stage t % NSTAGE, round = t / NSTAGE
     for (int t = 0; t < T; ++t) {
-      const int stage = t % NSTAGE;
-      float4 a_cur[2] = {a_reg[0], a_reg[1]};
-      float4 bh_cur[2] = {bh_reg[0], bh_reg[1]}, bl_cur[2] = {bl_reg[0], bl_reg[1]};
-      if (t + 1 < T) issue_loads();                               // next slab's loads fly while this one is stored
-      if (t >= NSTAGE) mbar_wait(&empty_bar[stage], ((t / NSTAGE) - 1) & 1);
+      if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1);
       uint8_t* sbase = smem_raw + (size_t)stage * stage_bytes;
-      float4* a_hi = reinterpret_cast<float4*>(sbase);
-      float4* a_lo = reinterpret_cast<float4*>(sbase + a_bytes);
-      float4* b_hi = reinterpret_cast<float4*>(sbase + (PREC == 3 ? 2 : 1) * a_bytes);
-      float4* b_lo = reinterpret_cast<float4*>(sbase + (PREC == 3 ? 2 : 1) * a_bytes + b_bytes);
+      float4* a_hi = reinterpret_cast<float4*>(sbase) + a_item;
+      float4* a_lo = reinterpret_cast<float4*>(sbase + a_bytes) + a_item;
+      float4* b_hi = reinterpret_cast<float4*>(sbase + (PREC == 3 ? 2 : 1) * a_bytes) + tid;
+      float4* b_lo = reinterpret_cast<float4*>(sbase + (PREC == 3 ? 2 : 1) * a_bytes + b_bytes) + tid;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const float4 v = a_cur[i];
-        const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
-        a_hi[jqA * APL + rowA + 64 * i] = h;
-        if (PREC == 3) a_lo[jqA * APL + rowA + 64 * i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        const float4 v = a_reg[i];
+        const float4 h = make_float4(tf32_rn_finite(v.x), tf32_rn_finite(v.y), tf32_rn_finite(v.z), tf32_rn_finite(v.w));
+        a_hi[64 * i] = h;
+        if (PREC == 3) a_lo[64 * i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         if (b_on[i]) {
-          b_hi[tid + i * TC_THREADS] = bh_cur[i];
-          if (PREC == 3) b_lo[tid + i * TC_THREADS] = bl_cur[i];
+          b_hi[i * TC_THREADS] = bh_reg[i];
+          if (PREC == 3) b_lo[i * TC_THREADS] = bl_reg[i];
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy STS -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
+      // The next slab's loads are issued AFTER the fence (it drains the warp's outstanding loads, so loads issued before
+      // it cannot overlap anything) straight into the registers just stored: no second register set, no copies.
+      if (t + 1 < T) issue_loads();
+      if (++stage == NSTAGE) { stage = 0; ++round; }
     }
   } else if (lane == 0) {
     // ---------------------------------------------------------------- MMA issuer (one thread)
@@ -299,57 +317,69 @@ spconv_tc_kernel(const float* __restrict__ in, int ld_in, int cin4 /*ceil4(cin)*
 }
 
 // out[row, col] = bias + sum_z partial[z][row][col] (fixed z order), plus the per-64-row-tile BN statistics.
-// One CTA per 64-row tile; 256 threads = 8 row lanes x 32 float4 column lanes, so a thread has 8 x splits independent
-// 16-byte loads in flight (the first version walked 16 rows x splits scalar loads per thread: 34 us per launch, as
-// long as the convolution it finished).
+// One CTA per (64-row tile, 128-column chunk); 256 threads = 8 row lanes x 32 float4 column lanes.  For every split z a
+// thread issues the loads of its 8 rows back to back and only then accumulates, so 8 (16 with the unroll) independent
+// 16-byte loads are in flight per thread and a launch needs `splits` dependent round trips.  (v1 walked 16 rows x splits
+// scalar loads per thread: 34 us; v2 nested the split loop inside the row loop -- 8 x splits round trips, 50-60 us on
+// the 2-11 CTA grids of the coarse levels, longer than the convolution it finished,
+// profiles/r01_launches_v7_one_fragment_summary.txt.)  Same summation order as before: bit-identical results.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, int m_out, int npad, int cout,
                      const float* __restrict__ bias, float* __restrict__ out, int ld_out, float* __restrict__ bn_partial) {
   __shared__ float s_s[8][128], s_q[8][128];
   const int cq = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int row0 = blockIdx.x * 64;
+  const int c0 = blockIdx.y * 128;
   const size_t plane = (size_t)m_out * npad;
-  for (int c0 = 0; c0 < cout; c0 += 128) {
-    const int col = c0 + cq * 4;
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-    if (col < npad && col < cout) {
-      float bv[4];
+  const int col = c0 + cq * 4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col < npad && col < cout) {
+    float4 v[8];
+    const float* p[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = (bias && col + j < cout) ? bias[col + j] : 0.f;
+    for (int i = 0; i < 8; ++i) {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int row = row0 + ry + 8 * i;
+      p[i] = row < m_out ? partial + (size_t)row * npad + col : nullptr;
+    }
+#pragma unroll 2
+    for (int z = 0; z < splits; ++z) {
+      float4 t[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = row0 + ry + 8 * i;
-        if (row < m_out) {
-          const float* p = partial + (size_t)row * npad + col;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int z = 0; z < splits; ++z) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p + (size_t)z * plane));
-            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      for (int i = 0; i < 8; ++i)
+        t[i] = p[i] ? __ldg(reinterpret_cast<const float4*>(p[i] + (size_t)z * plane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i].x += t[i].x; v[i].y += t[i].y; v[i].z += t[i].z; v[i].w += t[i].w; }
+    }
+    float bv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bv[j] = (bias && col + j < cout) ? bias[col + j] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + ry + 8 * i;
+      if (row < m_out) {
+        const float r[4] = {v[i].x + bv[0], v[i].y + bv[1], v[i].z + bv[2], v[i].w + bv[3]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < cout) {
+            out[(size_t)row * ld_out + col + j] = r[j];
+            s[j] += r[j];
+            q[j] = fmaf(r[j], r[j], q[j]);
           }
-          const float r[4] = {v.x + bv[0], v.y + bv[1], v.z + bv[2], v.w + bv[3]};
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col + j < cout) {
-              out[(size_t)row * ld_out + col + j] = r[j];
-              s[j] += r[j];
-              q[j] = fmaf(r[j], r[j], q[j]);
-            }
-        }
       }
     }
-    if (bn_partial) {
+  }
+  if (bn_partial) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { s_s[ry][cq * 4 + j] = s[j]; s_q[ry][cq * 4 + j] = q[j]; }
-      __syncthreads();
-      if (threadIdx.x < 128 && c0 + (int)threadIdx.x < cout) {
-        const int t = threadIdx.x;
-        float a = 0.f, b = 0.f;
+    for (int j = 0; j < 4; ++j) { s_s[ry][cq * 4 + j] = s[j]; s_q[ry][cq * 4 + j] = q[j]; }
+    __syncthreads();
+    if (threadIdx.x < 128 && c0 + (int)threadIdx.x < cout) {
+      const int t = threadIdx.x;
+      float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { a += s_s[r][t]; b += s_q[r][t]; }   // fixed order: deterministic
-        bn_partial[((size_t)blockIdx.x * 2 + 0) * cout + c0 + t] = a;
-        bn_partial[((size_t)blockIdx.x * 2 + 1) * cout + c0 + t] = b;
-      }
-      __syncthreads();
+      for (int r = 0; r < 8; ++r) { a += s_s[r][t]; b += s_q[r][t]; }   // fixed order: deterministic
+      bn_partial[((size_t)blockIdx.x * 2 + 0) * cout + c0 + t] = a;
+      bn_partial[((size_t)blockIdx.x * 2 + 1) * cout + c0 + t] = b;
     }
   }
 }
@@ -364,8 +394,9 @@ inline int pow2_cols(int n) {
 
 extern "C" {
 
-// Weights must be pre-arranged as float[K][nq][npad][4] (w[k][q][n][i] = W[k][4q+i][n], zero padded; npad = cout
-// rounded up to a multiple of 16, and of 128 when larger than 128).  w_lo is only read when prec == 3.
+// Weights must be pre-arranged as float[K][nq][npad][4] (w[k][q][n][i] = W[k][4q+i][n], zero padded; nq = ceil(cin/4)
+// rounded up to a multiple of 4 (whole 16-channel slabs); npad = cout rounded up to a multiple of 16, and of 128 when
+// larger than 128).  w_lo is only read when prec == 3.
 // bn_partial: NULL or float[ep_spconv_num_row_tiles(m_out), 2, cout].
 // split-K factor for small problems: spread the K kernel offsets over up to ~one wave of CTAs
 // EPRECON_TC_SPLIT_CTAS=<n> (experiment knob): aim for ~n CTAs per launch instead of one per SM, rounding the factor up
@@ -429,14 +460,14 @@ int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, in
   dim3 grid(ep_div_up(m_out, TMR), npad / nt, splits);
   const int bn_rows = ep_div_up(m_out, 64);
   if (prec == 3)
-    spconv_tc_kernel<3><<<grid, TC_THREADS + 32, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, (cin + 3) / 4, npad, nt,
+    spconv_tc_kernel<3><<<grid, TC_THREADS + 32, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, ((cin + 15) / 16) * 4, npad, nt,
                                                            tmem_cols, cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial);
   else
-    spconv_tc_kernel<1><<<grid, TC_THREADS + 32, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, (cin + 3) / 4, npad, nt,
+    spconv_tc_kernel<1><<<grid, TC_THREADS + 32, smem, stream>>>(in, ld_in, cin4, nbr, K, w_hi, w_lo, ((cin + 15) / 16) * 4, npad, nt,
                                                            tmem_cols, cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial);
   if (splits > 1)
-    splitk_reduce_kernel<<<ep_div_up(m_out, 64), 256, 0, stream>>>(partial, splits, (int)m_out, npad, cout, bias, out, ld_out,
-                                                                  bn_partial);
+    splitk_reduce_kernel<<<dim3(ep_div_up(m_out, 64), ep_div_up(cout, 128)), 256, 0, stream>>>(partial, splits, (int)m_out, npad, cout,
+                                                                                              bias, out, ld_out, bn_partial);
   EP_CHECK_LAUNCH();
   return EP_OK;
 }

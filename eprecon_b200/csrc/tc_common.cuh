@@ -65,6 +65,13 @@ __device__ __forceinline__ float tf32_round(float x) {  // round-to-nearest to 1
   return __uint_as_float(u);
 }
 
+// Same rounding (nearest, ties away from zero, to 10 mantissa bits) for FINITE inputs in two integer instructions:
+// cvt.rna.tf32.f32 has no single SASS instruction on sm_100a (it expands to an Inf/NaN guard + add + select + mask per
+// element: 32 of the ~200 instructions of a producer iteration).  Features and weights on this path are finite.
+__device__ __forceinline__ float tf32_rn_finite(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -287,7 +287,7 @@ _UMMA_CACHE = {}
 
 
 def _umma_weights(W, cout, prec):
-    """FFMA-layout weights [K, cin, ceil4(cout)] -> (w_hi, w_lo, npad) in the UMMA slab layout [K][ceil(cin/4)][npad][4]."""
+    """FFMA-layout weights [K, cin, ceil4(cout)] -> (w_hi, w_lo, npad) in the UMMA slab layout [K][nq][npad][4], nq = 4 * ceil(cin / 16)."""
     key = (W.data_ptr(), W._version, tuple(W.shape), prec)
     hit = _UMMA_CACHE.get(key)
     if hit is None:
@@ -295,7 +295,7 @@ def _umma_weights(W, cout, prec):
         npad = (cout + 15) // 16 * 16
         if npad > 128:
             npad = (cout + 127) // 128 * 128
-        nq = (cin + 3) // 4
+        nq = (cin + 15) // 16 * 4          # quads of input channels, zero-padded to whole 16-channel slabs
         wp = torch.zeros((K, nq * 4, npad), dtype=torch.float32, device=W.device)
         wp[:, :cin, :cout] = W[:, :, :cout]
         u = wp.view(torch.int32)

@@ -110,7 +110,7 @@ int ep_spconv_num_row_tiles(int64_t m_out);
 int ep_spconv_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, int K, const float* W, int ldw, int cout,
                   const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, cudaStream_t stream);
 /* tensor-core variant: tcgen05.mma kind::tf32, fp32 accumulators in TMEM; prec 1 = tf32, 3 = 3xTF32 split (fp32-grade).
- * w_hi / w_lo: float[K][ceil(cin/4)][npad][4] (see csrc/spconv_tc.cu). */
+ * w_hi / w_lo: float[K][nq][npad][4], nq = 4 * ceil(cin / 16): zero-padded to whole 16-channel slabs (see csrc/spconv_tc.cu). */
 size_t ep_spconv_tc_workspace_bytes(int64_t m_out, int npad, int K);
 int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, int K, const float* w_hi,
                      const float* w_lo, int npad, int cout, const float* bias, float* out, int ld_out, int64_t m_out,

@@ -359,6 +359,8 @@ class FusionState:
         self.F = [None] * 3
         self.tC = [None] * 3
         self.tF = [None] * 3
+        self.I = torch.zeros(0, dtype=torch.int32)   # global instance / semantic id per row of C[n_scales] (direct substitute)
+        self.S = torch.zeros(0, dtype=torch.int32)
 
 
 def _dense(locs, vals, dims, c, default):
@@ -368,8 +370,45 @@ def _dense(locs, vals, dims, c, default):
     return d
 
 
-def gru_fusion(state, sd, cfg, coords, values_in, inputs, scale, ch_voxel, direct_substitute=False):
-    """GRUFusion.forward (models/gru_fusion.py:259-394) for bs == 1, FUSION.FULL, without the panoptic volumes.
+def _common_rows(a, b):
+    """Number of coincident points of two coordinate lists with unique rows (compute_overlap's `distances == 0`)."""
+    key = lambda x: ((x[:, 0].long() + 4096) * 8192 + (x[:, 1].long() + 4096)) * 8192 + (x[:, 2].long() + 4096)  # noqa: E731
+    return int(np.intersect1d(key(a).numpy(), key(b).numpy()).size)
+
+
+def panoptic_fusion(state, scale, valid, rel, seg_u, info, upd, stuff_max=2, overlap_threshold=0.05):
+    """GRUFusion.panoptic_fusion + compute_overlap (models/gru_fusion.py:116-193): relabel the fragment's segments with
+    scene-level instance ids -- a thing segment takes the id of the first (ascending id) scene instance of its class
+    that overlaps it with IoU > 0.05, else a new id; stuff segments take their class id."""
+    cur = upd + rel
+    gI, gS = state.I[valid], state.S[valid]
+    max_id = max(int(state.I.max()), stuff_max) if len(state.I) > 0 else stuff_max
+    new_i, new_s = torch.zeros_like(seg_u), torch.zeros_like(seg_u)
+    inc = 1
+    for i, d in enumerate(info):
+        cls, sel = int(d["category_id"]), seg_u == i + 1
+        if not d["isthing"]:
+            new_i[sel], new_s[sel] = cls, cls
+            continue
+        matched = False
+        if bool((gS == cls).any()):
+            for ins in torch.unique(gI[gS == cls]).tolist():
+                a, b = state.C[scale][state.I == ins], cur[sel]
+                inter = _common_rows(a, b)
+                union = len(a) + len(b) - inter
+                if union > 0 and f32(inter) / f32(union) > f32(overlap_threshold):
+                    new_i[sel], new_s[sel] = int(ins), cls
+                    matched = True
+                    break
+        if not matched:
+            new_i[sel], new_s[sel] = max_id + inc, cls
+            inc += 1
+    return new_i, new_s
+
+
+def gru_fusion(state, sd, cfg, coords, values_in, inputs, scale, ch_voxel, direct_substitute=False, panoptic_info=None):
+    """GRUFusion.forward (models/gru_fusion.py:259-394) for bs == 1, FUSION.FULL.  With `panoptic_info` (direct
+    substitute only: {'panoptic_seg': [seg int32 [N], segments_info]}) the scene instance / semantic ids are fused too.
     Returns (coords int64 [U,4], values [U,C], tsdf_target [U,1], occ_target [U,1])."""
     interval = 2 ** (cfg.N_LAYER - scale - 1)
     scene = inputs["scene"][0]
@@ -379,6 +418,7 @@ def gru_fusion(state, sd, cfg, coords, values_in, inputs, scale, ch_voxel, direc
         c = 1 if direct_substitute else values_in.shape[1]
         state.C[scale], state.F[scale] = torch.zeros(0, 3, dtype=torch.long), torch.zeros(0, c)
         state.tC[scale], state.tF[scale] = torch.zeros(0, 3, dtype=torch.long), torch.zeros(0, 1)
+        state.I, state.S = torch.zeros(0, dtype=torch.int32), torch.zeros(0, dtype=torch.int32)
     origin = inputs["vol_origin_partial"][0]
     voxel_size = cfg.VOXEL_SIZE * interval
     rel = ((origin - state.origin[scale]) / voxel_size).long()
@@ -396,16 +436,26 @@ def gru_fusion(state, sd, cfg, coords, values_in, inputs, scale, ch_voxel, direc
     else:
         upd = torch.nonzero((gvol != 0).any(-1) | (cvol != 0).any(-1))
     lvl = cfg.N_LAYER - scale - 1
-    occ_t = inputs["occ_list"][lvl][0]
-    tsdf_t = inputs["tsdf_list"][lvl][0][occ_t]
-    tC = state.tC[scale] - rel
-    valid_t = ((tC < dim) & (tC >= 0)).all(-1)
-    tvol = _dense(torch.cat([tC[valid_t], torch.nonzero(occ_t)])[:, :3],
-                  torch.cat([state.tF[scale][valid_t], tsdf_t.unsqueeze(-1)]), dims, 1, 1)
+    has_gt = "occ_list" in inputs
+    if has_gt:
+        occ_t = inputs["occ_list"][lvl][0]
+        tsdf_t = inputs["tsdf_list"][lvl][0][occ_t]
+        tC = state.tC[scale] - rel
+        valid_t = ((tC < dim) & (tC >= 0)).all(-1)
+        tvol = _dense(torch.cat([tC[valid_t], torch.nonzero(occ_t)])[:, :3],
+                      torch.cat([state.tF[scale][valid_t], tsdf_t.unsqueeze(-1)]), dims, 1, 1)
     values = cvol[upd[:, 0], upd[:, 1], upd[:, 2]]
     gvalues = gvol[upd[:, 0], upd[:, 1], upd[:, 2]]
-    tsdf_target = tvol[upd[:, 0], upd[:, 1], upd[:, 2]]
-    occ_target = tsdf_target.abs() < 1
+    tsdf_target = tvol[upd[:, 0], upd[:, 1], upd[:, 2]] if has_gt else None
+    occ_target = tsdf_target.abs() < 1 if has_gt else None
+    if direct_substitute and panoptic_info is not None:
+        # gru_fusion.py:352-363: the fragment's segment ids at the union sites (0 where only the scene has a voxel)
+        seg, info = panoptic_info["panoptic_seg"]
+        svol = torch.zeros(dims, dtype=seg.dtype)
+        svol[coords_b[:, 0], coords_b[:, 1], coords_b[:, 2]] = seg
+        new_i, new_s = panoptic_fusion(state, scale, valid, rel, svol[upd[:, 0], upd[:, 1], upd[:, 2]], info, upd)
+        state.I = torch.cat([state.I[valid == False], new_i.to(torch.int32)])  # noqa: E712
+        state.S = torch.cat([state.S[valid == False], new_s.to(torch.int32)])  # noqa: E712
     if not direct_substitute:
         cv = ch_voxel[scale]
         vres = cfg.VOXEL_SIZE * 2 ** (len(cfg.THRESHOLDS) - 1 - scale)
@@ -416,9 +466,10 @@ def gru_fusion(state, sd, cfg, coords, values_in, inputs, scale, ch_voxel, direc
         values = torch.cat([vv, vi], -1)
     state.F[scale] = torch.cat([state.F[scale][valid == False], values])  # noqa: E712
     state.C[scale] = torch.cat([state.C[scale][valid == False], upd + rel])  # noqa: E712
-    tv = tvol.squeeze(-1)
-    state.tF[scale] = torch.cat([state.tF[scale][valid_t == False], tv[tv.abs() < 1].unsqueeze(-1)])  # noqa: E712
-    state.tC[scale] = torch.cat([state.tC[scale][valid_t == False], torch.nonzero(tv.abs() < 1) + rel])  # noqa: E712
+    if has_gt:
+        tv = tvol.squeeze(-1)
+        state.tF[scale] = torch.cat([state.tF[scale][valid_t == False], tv[tv.abs() < 1].unsqueeze(-1)])  # noqa: E712
+        state.tC[scale] = torch.cat([state.tC[scale][valid_t == False], torch.nonzero(tv.abs() < 1) + rel])  # noqa: E712
     out_c = torch.cat([torch.zeros(len(upd), 1, dtype=upd.dtype), upd * interval], 1)
     return out_c, values, tsdf_target, occ_target
 

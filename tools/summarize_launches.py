@@ -45,10 +45,15 @@ def main():
         scale = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}.get(unit, 1e-3)
         rows.append((r[header["Kernel Name"]], val * scale))
     marks = [i for i, (k, _) in enumerate(rows) if "init_prune_kernel" in k]
-    if len(marks) < back + 1:
-        raise SystemExit(f"only {len(marks)} fragments in the list")
-    lo, hi = marks[-back - 1], marks[-back]
-    seg = rows[lo:hi]
+    if len(marks) <= 1:
+        # `ncu --profile-from-start off`: bench.py brackets exactly one steady-state fragment with cudaProfilerStart/Stop
+        lo, hi, seg = 0, len(rows), rows
+        marks, back = [0], 0
+    else:
+        if len(marks) < back + 1:
+            raise SystemExit(f"only {len(marks)} fragments in the list")
+        lo, hi = marks[-back - 1], marks[-back]
+        seg = rows[lo:hi]
     agg = collections.defaultdict(lambda: [0.0, 0])
     for k, us in seg:
         a = agg[short(k)]
