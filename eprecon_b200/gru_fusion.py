@@ -8,7 +8,12 @@ gathers, and the ConvGRUs of a level share one set of voxelisations / kernel map
 
 Ground-truth bookkeeping (target_tsdf_volume; only used for the reference's loss and its "GT occupancy overlaps
 prediction" guard, models/neucon_network.py:486-490) stays a small dense 1-channel volume in plain torch.
-`panoptic_fusion` / instance-semantic volumes are outside this round's scope.
+Panoptic global fusion (direct-substitute mode with `panoptic_infos`; gru_fusion.py:116-193,352-369; SURVEY.md
+section 8 f2): the reference computes the IoU of every (fragment segment, scene instance) candidate pair with an
+M x N pairwise distance matrix (`compute_overlap`) inside a host loop with `.item()` reads.  Here the union kernel
+already knows, for every union site, the row of the scene voxel at the same coordinate (`row_b`), so all pair
+intersections are ONE bincount over (segment id, scene instance id) and the host loop runs on three small tables
+read back once.
 """
 import torch
 import torch.nn as nn
@@ -38,6 +43,8 @@ class GRUFusion(nn.Module):
         self.global_origin = [None, None, None]
         self.global_volume = [None, None, None]      # dict(C int32 [Ng,3] global voxel ids, F fp32 [Ng,C])
         self.target_tsdf_volume = [None, None, None]
+        self.global_instance = None                   # int32 [Ng] scene instance / semantic id per row of the finest
+        self.global_semantic = None                   # global volume (direct substitute + panoptic_infos only)
         self.return_int32 = False
         self._consts = {}
         if direct_substitute:
@@ -69,6 +76,66 @@ class GRUFusion(nn.Module):
                                  "F": torch.zeros((0, ops.ceil4(c)), dtype=torch.float32, device=device)}
         self.target_tsdf_volume[i] = {"C": torch.zeros((0, 3), dtype=torch.int64, device=device),
                                       "F": torch.zeros((0, 1), dtype=torch.float32, device=device)}
+        self.global_instance = torch.zeros(0, dtype=torch.int32, device=device)
+        self.global_semantic = torch.zeros(0, dtype=torch.int32, device=device)
+
+    # ------------------------------------------------------------------------------------------------
+    def panoptic_fusion(self, scale, global_valid, relative_origin, panoptic_info, current_coords, row_b=None):
+        """gru_fusion.py:133-193 (+ compute_overlap :116-131).  panoptic_info['panoptic_seg'] = [segment id per union
+        site int32 [U], segments_info]; `row_b` int32 [U] = row of the scene voxel at the same coordinate (-1: none).
+        Returns (new_current_instance, new_current_semantic) int32 [U].  A thing segment takes the id of the first
+        (ascending) scene instance of its class whose IoU with it exceeds 0.05, else a fresh id; stuff takes its class id."""
+        seg, info = panoptic_info["panoptic_seg"]
+        dev = seg.device
+        n_seg = len(info)
+        gi, gs = self.global_instance, self.global_semantic
+        stuff_max, thr = 2, 0.05
+        seg_l = seg.long()
+        if gi.shape[0] > 0 and n_seg > 0:
+            top = torch.stack([gi.max(), gs.max()]).tolist()                      # host read 1: table extents
+            m_ins, m_sem = int(top[0]) + 1, int(top[1]) + 1
+            hit = row_b >= 0
+            pair = torch.bincount(seg_l[hit] * m_ins + gi[row_b[hit].long()].long(), minlength=(n_seg + 1) * m_ins)
+            area_seg = torch.bincount(seg_l, minlength=n_seg + 1)[: n_seg + 1]
+            area_ins = torch.bincount(gi.long(), minlength=m_ins)
+            gv = global_valid.nonzero().squeeze(1)
+            present = torch.bincount(gs[gv].long() * m_ins + gi[gv].long(), minlength=m_sem * m_ins)
+            host = torch.cat([pair, area_seg, area_ins, present]).tolist()        # host read 2: all pair statistics
+            o = 0
+            pair_h = host[o:o + (n_seg + 1) * m_ins]; o += (n_seg + 1) * m_ins    # noqa: E702
+            aseg_h = host[o:o + n_seg + 1]; o += n_seg + 1                        # noqa: E702
+            ains_h = host[o:o + m_ins]; o += m_ins                                # noqa: E702
+            pres_h = host[o:o + m_sem * m_ins]
+            max_id = max(m_ins - 1, stuff_max)
+        else:
+            m_ins = m_sem = 0
+            pair_h = aseg_h = ains_h = pres_h = []
+            max_id = max(int(gi.max()), stuff_max) if gi.shape[0] > 0 else stuff_max
+        tab_i, tab_s = [0] * (n_seg + 1), [0] * (n_seg + 1)
+        inc = 1
+        f32 = lambda v: torch.tensor(float(v), dtype=torch.float32)  # noqa: E731   (the reference divides int64 tensors)
+        for i, d in enumerate(info):
+            cls = int(d["category_id"])
+            if not d["isthing"]:
+                tab_i[i + 1] = tab_s[i + 1] = cls
+                continue
+            matched = False
+            if cls < m_sem:
+                for ins in range(m_ins):                                          # ascending, as torch.unique
+                    if not pres_h[cls * m_ins + ins]:
+                        continue
+                    inter = pair_h[(i + 1) * m_ins + ins]
+                    union = aseg_h[i + 1] + ains_h[ins] - inter
+                    if union > 0 and bool(f32(inter) / f32(union) > thr):
+                        tab_i[i + 1], tab_s[i + 1] = ins, cls
+                        matched = True
+                        break
+            if not matched:
+                tab_i[i + 1], tab_s[i + 1] = max_id + inc, cls
+                inc += 1
+        ti = torch.tensor(tab_i, dtype=torch.int32, device=dev)
+        tsm = torch.tensor(tab_s, dtype=torch.int32, device=dev)
+        return ti[seg_l], tsm[seg_l]
 
     # ------------------------------------------------------------------------------------------------
     def _union(self, coords_b4, values, c, rel, dims, scale, batch, interval):
@@ -147,11 +214,13 @@ class GRUFusion(nn.Module):
         """Scene TSDF as a dense bounding-box volume (gru_fusion.py:217-257), TSDF channel only."""
         if outputs is None:
             outputs = dict()
+        keys = ("origin", "scene_tsdf", "scene_name", "scene_instance", "scene_semantic")
         if "scene_name" not in outputs:
-            outputs["origin"], outputs["scene_tsdf"], outputs["scene_name"] = [], [], []
+            for k in keys:
+                outputs[k] = []
         if scene in outputs["scene_name"]:
             idx = outputs["scene_name"].index(scene)
-            for k in ("origin", "scene_tsdf", "scene_name"):
+            for k in keys:
                 del outputs[k][idx]
         outputs["scene_name"].append(scene)
         g = self.global_volume[scale]
@@ -163,6 +232,11 @@ class GRUFusion(nn.Module):
         vol = torch.full(dim, 1.0, dtype=torch.float32, device=c.device)
         vol[ind[:, 0], ind[:, 1], ind[:, 2]] = g["F"][:, 0]
         outputs["scene_tsdf"].append(vol)
+        for key, ids in (("scene_instance", self.global_instance), ("scene_semantic", self.global_semantic)):
+            v = torch.zeros(dim, dtype=torch.int32, device=c.device)
+            if ids is not None and ids.shape[0] == c.shape[0]:          # fused with panoptic_infos (gru_fusion.py:251-256)
+                v[ind[:, 0], ind[:, 1], ind[:, 2]] = ids
+            outputs[key].append(v)
         return outputs
 
     @torch.no_grad()
@@ -227,6 +301,16 @@ class GRUFusion(nn.Module):
                     out_v = gru_v.run(gvalues[:, :cv], values[:, :cv], pc1, pc2)
                     out_i = gru_i.run(gvalues[:, cv:c_all], values[:, cv:c_all], pc1, pc2)
                     values = torch.cat([out_v[:, :cv], out_i[:, :c_all - cv]], dim=-1)
+            new_inst = new_sem = None
+            if self.direct_substitude and panoptic_infos is not None:
+                # gru_fusion.py:352-363: the fragment's segment ids at the union sites (0 where only the scene has a voxel)
+                info = panoptic_infos[i]
+                seg = info["panoptic_seg"][0].to(torch.int32)
+                if batch_size > 1:
+                    seg = seg[sel]
+                info["panoptic_seg"][0] = torch.where(row_a >= 0, seg[row_a.clamp_min(0).long()], torch.zeros((), dtype=torch.int32, device=dev))
+                new_inst, new_sem = self.panoptic_fusion(scale=scale, global_valid=valid, relative_origin=rel, panoptic_info=info,
+                                                         current_coords=upd[:, 1:], row_b=row_b)
             # update_map (gru_fusion.py:195-204): drop in-volume global rows, append the fused ones
             relt = self._const(tuple(rel), dev, torch.int32)
             vpad = values if values.shape[1] == g["F"].shape[1] else torch.nn.functional.pad(
@@ -235,8 +319,13 @@ class GRUFusion(nn.Module):
                 stay = torch.nonzero(valid == False).squeeze(1)  # noqa: E712  (one size read-back for both gathers)
                 g["F"] = torch.cat([g["F"][stay], vpad])
                 g["C"] = torch.cat([g["C"][stay], upd[:, 1:] + relt])
+                if new_inst is not None:
+                    self.global_instance = torch.cat([self.global_instance[stay], new_inst])
+                    self.global_semantic = torch.cat([self.global_semantic[stay], new_sem])
             else:
                 g["F"], g["C"] = vpad, upd[:, 1:] + relt
+                if new_inst is not None:
+                    self.global_instance, self.global_semantic = new_inst, new_sem
             out_c = upd.clone()
             out_c[:, 1:] *= interval
             coords_all.append(out_c)

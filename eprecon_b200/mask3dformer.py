@@ -1,6 +1,6 @@
 """Panoptic decoder — drop-in for models/mask3dformer.py (MultiScaleMaskedTransformerDecoder.forward :338-429,
-forward_prediction_heads :431-447, panoptic_post / panoptic_inference :461-581) and the Fourier voxel position encoding
-(models/voxel_position_encoding.py:43-70,116-146).  SURVEY.md section 8(f) row 1: first widening after the TSDF path.
+forward_prediction_heads :431-447, panoptic_post / panoptic_inference :462-581) and the Fourier voxel position encoding
+(models/voxel_position_encoding.py:42-70,116-146).  SURVEY.md section 8(f) row 1: first widening after the TSDF path.
 
 Same constructor keywords, forward() signature, output dict and state-dict names as the reference
 (`query_feat`, `query_embed`, `transformer_{self,cross}_attention_layers.N.{self_attn,multihead_attn}.in_proj_*`,

@@ -128,3 +128,31 @@ def test_neucon_forward_with_panoptic_head(cuda_lib):
     wseg, winfo = restate.panoptic_inference(want["pred_logits"], want["pred_masks"])
     assert (seg.cpu() != wseg).float().mean().item() <= 1e-3
     assert [d["category_id"] for d in info] == [d["category_id"] for d in winfo]
+
+
+def test_direct_substitute_panoptic_fusion_matches_reference(cuda_lib):
+    """GRUFusion(direct_substitute=True) with panoptic_infos over three overlapping fragments -- scene
+    TSDF, instance and semantic ids equal the UNMODIFIED reference's (tests/golden/panoptic_fusion_small.npz), bit-exact."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from make_golden_panoptic_fusion import N_VOX, fusion_inputs
+    from eprecon_b200.gru_fusion import GRUFusion
+    g = np.load(os.path.join(HERE, "golden", "panoptic_fusion_small.npz"))
+    cfg = synth.make_cfg(n_vox=N_VOX)
+    fuse = GRUFusion(cfg, direct_substitute=True, trianing=False)
+    outputs = {}
+    for frag in range(3):
+        inputs, coords, tsdf, info = fusion_inputs(frag)
+        cin = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inputs.items() if k not in ("occ_list", "tsdf_list")}
+        pinfo = {"panoptic_seg": [info["panoptic_seg"][0].cuda(), info["panoptic_seg"][1]]}
+        outputs = fuse(coords.cuda(), tsdf.cuda(), cin, 2, outputs, save_mesh=True, panoptic_infos=[pinfo])
+        C = fuse.global_volume[2]["C"].cpu().long()
+        key = (C[:, 0] * 100000 + C[:, 1]) * 100000 + C[:, 2]
+        o = torch.argsort(key)
+        assert np.array_equal(C[o].numpy(), g[f"f{frag}_gC"]), frag
+        assert np.array_equal(fuse.global_volume[2]["F"][:, :1].cpu()[o].numpy(), g[f"f{frag}_gF"]), frag
+        assert np.array_equal(fuse.global_instance.cpu()[o].numpy().reshape(-1, 1), g[f"f{frag}_gI"]), frag
+        assert np.array_equal(fuse.global_semantic.cpu()[o].numpy().reshape(-1, 1), g[f"f{frag}_gS"]), frag
+        assert tuple(outputs["scene_tsdf"][-1].shape) == tuple(int(v) for v in g[f"f{frag}_scene_shape"])
+        assert np.array_equal(np.bincount(outputs["scene_instance"][-1].cpu().long().flatten().numpy()), g[f"f{frag}_scene_instance_hist"])
+        assert np.array_equal(np.bincount(outputs["scene_semantic"][-1].cpu().long().flatten().numpy()), g[f"f{frag}_scene_semantic_hist"])
