@@ -34,9 +34,10 @@ FULL_NOTE = ("value / 31: the oracle's full 3-level fragment took 130 s vs 4.2 s
              "level 2 (210 k candidate voxels) is skipped in the timed sample to keep the run within minutes")
 METRIC = "fragments/sec (9x640x480, 3-level 96^3)"
 DEFAULT_STREAMS = 8   # fragments in flight per GPU (EPRECON_STREAMS overrides); 1/4/8 streams measured 44/70/81 fragments/s
-# dram__bytes_read.sum + dram__bytes_write.sum of one level-2 spconv_tc_kernel<3> launch (ncu --set full)
-SPCONV_TRAFFIC = {"bytes": 41.3e6, "note": "dram read+write bytes of one level-2 launch (74->8 ch, 200k rows) from "
-                                           "profiles/r01_spconv_tc_v2_ncu_summary.csv"}
+# dram__bytes_read.sum + dram__bytes_write.sum of the largest spconv_tc_kernel<3> launch of a fragment (ncu --set full)
+SPCONV_TRAFFIC = {"bytes": 84.4e6, "note": "dram read 80.0 MB + write 4.4 MB of the level-2 stem launch (74->8 ch, 193 k rows, K=27; "
+                                           "algorithmic bytes of that launch: 57 MB rows in + 6 MB rows out + 21 MB neighbour table "
+                                           "= 84 MB, i.e. no DRAM re-reads) from profiles/r01_spconv_tc_v7_level2_ncu_summary.txt"}
 WORKLOAD = "configs[1]: single 9-view 640x480 fragment, 3-level 24/48/96^3 @4cm, GRU fusion (fresh scene), TSDF+occ heads"
 
 

@@ -100,3 +100,24 @@ def test_executor_descriptors_parse_natively():
     bad = arr.copy()
     bad[-1] = 0                                                        # broken end marker -> rejected
     assert L.ep_exec_desc_check(3, bad.ctypes.data) < 0
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree (build container only)")
+def test_state_dict_keys_and_shapes_equal_the_reference_module():
+    """Every parameter / buffer of the drop-in NeuConNet exists under the same name and shape in the UNMODIFIED reference
+    NeuConNet (incl. the panoptic decoder), so reference checkpoints load by name."""
+    from oracle import ref_import
+    from eprecon_b200 import synth
+    from eprecon_b200.neucon_network import NeuConNet
+    ns = ref_import.load()
+    cfg = synth.make_cfg()
+    ref = {k: tuple(v.shape) for k, v in ns.neucon.NeuConNet(cfg).state_dict().items()}
+    ours = {k: tuple(v.shape) for k, v in NeuConNet(cfg).state_dict().items()}
+    missing = [k for k in ours if k not in ref]
+    assert not missing, missing[:10]
+    wrong = [(k, ours[k], ref[k]) for k in ours if ours[k] != ref[k]]
+    assert not wrong, wrong[:10]
+    # what the reference has and the drop-in does not: only the training criterion (loss weights) and BN bookkeeping
+    extra = [k for k in ref if k not in ours and not k.startswith("criterion.") and not k.endswith("num_batches_tracked")]
+    assert not extra, extra[:10]
