@@ -16,12 +16,14 @@ What changes underneath:
   * attention masks are never expanded to [heads, Q, N] booleans: one [Q, N] mask is shared by the heads;
   * panoptic_inference does its per-query bookkeeping with three bincounts and ONE device->host read instead of
     three `.item()` syncs per query.
-The dense algebra of the decoder (80 queries x 48 channels against N voxels) is a handful of small fp32 GEMMs and
-soft-maxes on cuBLAS/ATen -- library calls like the dense 2-D fusion convs; a fused
-project-mask-softmax kernel over the keys is the next step for this row.
+  * the masked cross-attention over the voxel keys (6.2 of the decoder's 10 ms on the library route: batched GEMMs with
+    an inner dimension of 6) is one fused pass over the keys, `ep_masked_attention` (csrc/attention.cu).
+The remaining dense algebra (K/V projections [N,48]x[48,48], the 80 x 80 self-attention, FFN, prediction heads) is a
+handful of small fp32 GEMMs on cuBLAS/ATen -- library calls like the dense 2-D fusion convs.
 CUDA tensors only: there is no CPU path.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -29,6 +31,11 @@ import torch.nn.functional as F
 
 from . import ops
 from ._lib import EpreconError
+
+
+# cross-attention over the voxel keys through the fused kernel (csrc/attention.cu); the ATen formulation remains for the
+# 80 x 80 self-attention and for decoder shapes the kernel does not cover (head_dim != 6)
+FUSED_ATTENTION = os.environ.get("EPRECON_FUSED_ATTENTION", "1") != "0"
 
 
 def _need_cuda(t, what):
@@ -96,6 +103,13 @@ class _Attention(nn.Module):
 
     def attend(self, query_rows, key_rows, value_rows, blocked=None):
         E, h = self.embed_dim, self.num_heads
+        if FUSED_ATTENTION and E // h == 6 and h <= 8 and query_rows.shape[0] <= 96 and key_rows.shape[0] > query_rows.shape[0]:
+            # cross-attention over the voxel keys: one fused pass (score -> mask -> online softmax -> weighted sum,
+            # csrc/attention.cu) instead of [heads, Q, N] score tensors and two batched GEMMs with a dimension of 6
+            q = F.linear(query_rows, self.in_proj_weight[:E], self.in_proj_bias[:E])
+            k = F.linear(key_rows, self.in_proj_weight[E:2 * E], self.in_proj_bias[E:2 * E])
+            v = F.linear(value_rows, self.in_proj_weight[2 * E:], self.in_proj_bias[2 * E:])
+            return self.out_proj(ops.masked_attention(q, k, v, blocked, h, 1.0 / math.sqrt(E // h)))
         q = F.linear(query_rows, self.in_proj_weight[:E], self.in_proj_bias[:E]).view(-1, h, E // h).transpose(0, 1)
         k, v = self.project_memory(key_rows, value_rows)
         s = torch.matmul(q, k.transpose(1, 2)) * (1.0 / math.sqrt(E // h))       # [h, Q, N]

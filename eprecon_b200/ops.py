@@ -426,3 +426,26 @@ def threshold_flags(x, thr, mode=0):
     _lib.check(_L().ep_threshold_flags(x.data_ptr(), x.stride(0), n, float(thr), int(mode), flags.data_ptr(),
                                        stream_ptr()), "ep_threshold_flags")
     return flags
+
+
+def masked_attention(q, k, v, blocked, n_heads, scale):
+    """Fused masked cross-attention (csrc/attention.cu): q [Q, H*6], k / v [N, H*6] projected rows, blocked bool / uint8
+    [Q, N] (True = may not attend) or None -> [Q, H*6].  One pass over the keys, deterministic."""
+    L = _L()
+    q = _chk(q, torch.float32, "q")
+    k = _chk(k, torch.float32, "k")
+    v = _chk(v, torch.float32, "v")
+    nq, e = q.shape
+    n = k.shape[0]
+    if blocked is not None:
+        blocked = blocked.view(torch.uint8) if blocked.dtype == torch.bool else blocked
+        blocked = _chk(blocked, torch.uint8, "blocked")
+        assert tuple(blocked.shape) == (nq, n)
+    out = torch.empty((nq, e), dtype=torch.float32, device=q.device)
+    wsb = L.ep_masked_attention_workspace_bytes(n, n_heads)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=q.device)
+    _lib.check(L.ep_masked_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), k.stride(0), _ptr(blocked), n, nq, n_heads,
+                                     e // n_heads, float(scale), out.data_ptr(), ws.data_ptr(), wsb, stream_ptr()),
+               "ep_masked_attention")
+    return out
+

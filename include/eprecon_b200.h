@@ -161,6 +161,16 @@ int ep_mark_parents(const int32_t* coords, int64_t n, int step, int dx, int dy, 
 int ep_lookup_marks(const int32_t* coords, int64_t n, int step, int dx, int dy, int dz, int bs, const uint8_t* vol,
                     uint8_t* flags, cudaStream_t stream);
 
+/* ---- panoptic decoder: masked cross-attention (models/mask3dformer.py:70-130,392-397 over nn.MultiheadAttention).
+ * One pass over the keys: score -> mask -> online softmax -> weighted sum; per-chunk partials merged in fixed order.
+ * q [n_queries, n_heads*head_dim] projected + unscaled; k, v [n_keys, ld_kv] projected; blocked uint8 [n_queries, n_keys]
+ * (non-zero = the query may not attend to the key; NULL = no mask); out [n_queries, n_heads*head_dim].
+ * Supported: head_dim == 6, n_queries <= 96, n_heads <= 8 (the reference decoder: 48 channels, 8 heads, 80 queries). */
+size_t ep_masked_attention_workspace_bytes(int64_t n_keys, int n_heads);
+int ep_masked_attention(const float* q, const float* k, const float* v, int ld_kv, const uint8_t* blocked, int64_t n_keys,
+                        int n_queries, int n_heads, int head_dim, float scale, float* out, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
+
 /* ---- small index helpers used by the native executor --------------------------------------------------------
  * ep_csr_expand: segments of a (voxel id)-keyed sort -> dense per-voxel [s0, s1) ranges (s0/s1 pre-zeroed; the scatter
  * the reference gets from torchsparse spcount/spvoxelize, ops/torchsparse_utils.py:51-58).  ep_translate_index:

@@ -156,3 +156,31 @@ def test_direct_substitute_panoptic_fusion_matches_reference(cuda_lib):
         assert tuple(outputs["scene_tsdf"][-1].shape) == tuple(int(v) for v in g[f"f{frag}_scene_shape"])
         assert np.array_equal(np.bincount(outputs["scene_instance"][-1].cpu().long().flatten().numpy()), g[f"f{frag}_scene_instance_hist"])
         assert np.array_equal(np.bincount(outputs["scene_semantic"][-1].cpu().long().flatten().numpy()), g[f"f{frag}_scene_semantic_hist"])
+
+
+@pytest.mark.parametrize("n_keys,n_queries,n_heads", [(1, 80, 8), (63, 80, 8), (65, 96, 8), (5000, 80, 8), (105001, 80, 8), (777, 7, 2)])
+def test_fused_masked_attention_matches_fp64_softmax(cuda_lib, n_keys, n_queries, n_heads):
+    """csrc/attention.cu vs a float64 masked softmax-attention (the nn.MultiheadAttention math of mask3dformer.py:70-130)."""
+    from eprecon_b200 import ops
+    g = torch.Generator().manual_seed(n_keys)
+    E = n_heads * 6
+    q = torch.randn(n_queries, E, generator=g) * 2.0
+    k = torch.randn(n_keys, E, generator=g) * 2.0
+    v = torch.randn(n_keys, E, generator=g)
+    blocked = torch.rand(n_queries, n_keys, generator=g) < 0.6
+    blocked[:, 0] = False                                   # every query sees at least one key
+    if n_keys > 200:
+        blocked[3, 1:] = True                               # a query with a single visible key
+        blocked[5, 64:192] = True                           # whole tiles masked
+        blocked[:, 128:136] = True                          # a softmax block masked for every query
+    scale = 1.0 / 6 ** 0.5
+    qh = (q.double() * scale).view(n_queries, n_heads, 6).transpose(0, 1)
+    kh = k.double().view(n_keys, n_heads, 6).transpose(0, 1)
+    vh = v.double().view(n_keys, n_heads, 6).transpose(0, 1)
+    s = (qh @ kh.transpose(1, 2)).masked_fill(blocked.unsqueeze(0), float("-inf"))
+    want = (torch.softmax(s, -1) @ vh).transpose(0, 1).reshape(n_queries, E)
+    got = ops.masked_attention(q.cuda(), k.cuda(), v.cuda(), blocked.cuda(), n_heads, scale).cpu().double()
+    assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+    got2 = ops.masked_attention(q.cuda(), k.cuda(), v.cuda(), None, n_heads, scale).cpu().double()
+    want2 = (torch.softmax(qh @ kh.transpose(1, 2), -1) @ vh).transpose(0, 1).reshape(n_queries, E)
+    assert (got2 - want2).abs().max().item() <= 2e-5 * max(1.0, want2.abs().max().item())
