@@ -9,6 +9,7 @@ Layout
                spconv-cu117) -- PARITY UNPINNED, cross-checked against dense ATen ops.
   ref_import.py  imports the UNMODIFIED reference modules from /root/reference over those shims
                (build container only; /root/reference does not exist on the GPU box).
-  restate.py   self-contained functional restatement of the hot path (travels to the GPU box);
-               pinned against reference outputs via tests/golden/.
+  restate.py   self-contained functional restatement of the hot path and of the panoptic rows that hang
+               off it (travels to the GPU box); pinned against reference outputs via tests/golden/
+               (three fixtures; the two panoptic ones pin plain-ATen reference code directly).
 """

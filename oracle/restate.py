@@ -2,10 +2,13 @@
 
 Functional style (explicit state dicts, no nn.Module mirror) so that it can travel to the GPU box,
 where /root/reference does not exist.  Each function cites the reference lines it follows; the
-restatement is pinned against the UNMODIFIED reference (run over oracle/shims in the build container)
-by the fixtures in tests/golden/ (made by tests/golden/make_golden.py).  The third-party sparse-conv
-semantics underneath (torchsparse v2.0.0 / spconv) are restated from their published algorithms and
-are PARITY UNPINNED — see oracle/shims/torchsparse/__init__.py.
+restatement is pinned against the UNMODIFIED reference (run in the build container) by the fixtures in
+tests/golden/, each committed with the script that made it:
+  neucon_small.npz          NeuConNet.forward over oracle/shims (make_golden.py)
+  mask3dformer_small.npz    the panoptic decoder + panoptic_inference, plain ATen: a direct pin (make_golden_mask3dformer.py)
+  panoptic_fusion_small.npz GRUFusion(direct_substitute) + panoptic_fusion, plain ATen: a direct pin (make_golden_panoptic_fusion.py)
+The third-party sparse-conv semantics underneath the first fixture (torchsparse v2.0.0 / spconv) are restated
+from their published algorithms and are PARITY UNPINNED — see oracle/shims/torchsparse/__init__.py.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
 """
