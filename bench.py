@@ -28,10 +28,15 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# the oracle needs ~130 s for a FULL fragment on the 8-core build container vs 4.2 s for the timed sample (levels 0-1)
-FULL_OVER_SAMPLE = 31.0
-FULL_NOTE = ("value / 31: the oracle's full 3-level fragment took 130 s vs 4.2 s for this sample on the 8-core build container; "
-             "level 2 (210 k candidate voxels) is skipped in the timed sample to keep the run within minutes")
+# Share of a full fragment's oracle time that a truncated sample covers, measured on the 8-core build container
+# (oracle/restate.neucon_forward, max_level = 0 / 1 / 2: 1.27 s / 3.30 s / 21.8 s).  A sample that stops after level L
+# is reported as SAMPLE_FRACTION[L] fragments per step, so `value` stays in fragments/s of the FULL workload.
+SAMPLE_FRACTION = {0: 0.058, 1: 0.151, 2: 1.0}
+SAMPLE_TEXT = {2: "one FULL 9x640x480 fragment per step: occupancy initialisation + levels 0-2 (24^3, 48^3, 96^3) with GRU fusion and heads",
+               1: "per step: one full-size fragment through occupancy initialisation + levels 0-1 (24^3, 48^3); level 2 (96^3) skipped, "
+                  "counted as 0.151 of a fragment (its share of the oracle's time on the build container)",
+               0: "per step: one full-size fragment through occupancy initialisation + level 0 only (configs[0]); counted as 0.058 "
+                  "of a fragment (its share of the oracle's time on the build container)"}
 METRIC = "fragments/sec (9x640x480, 3-level 96^3)"
 DEFAULT_STREAMS = 8   # fragments in flight per GPU (EPRECON_STREAMS overrides); 1/4/8 streams measured 44/70/81 fragments/s
 # dram__bytes_read.sum + dram__bytes_write.sum of the largest spconv_tc_kernel<3> launch of a fragment (ncu --set full)
@@ -174,10 +179,9 @@ def _cpu_threads():
     return max(1, min(os.cpu_count() or 1, 16))
 
 
-def cpu_sample(steps, warmup, max_level=1):
-    """Oracle (port of the reference algorithm) on the host cores: one full-size fragment through the occupancy
-    initialisation and levels 0-1 (24^3 and 48^3).  Level 2 (96^3, ~95 % of the oracle's CPU time: ~2 min per fragment on
-    8 cores) is NOT run, so fragments/s computed from this sample is an UPPER bound on the CPU path."""
+def cpu_sample(steps, warmup, max_level=2):
+    """Oracle (port of the reference algorithm) on the host cores: `steps` full-size fragments through the occupancy
+    initialisation and levels 0..max_level; returns the mean seconds per step."""
     from oracle import restate
     from eprecon_b200 import synth
     from eprecon_b200.neucon_network import NeuConNet
@@ -199,27 +203,31 @@ def cpu_sample(steps, warmup, max_level=1):
     return sum(times) / len(times)
 
 
+def pick_sample_level(probe_l0_seconds, n_steps, budget_seconds):
+    """Largest truncation level whose estimated run (from a level-0 probe) fits the time budget."""
+    for lvl in (2, 1):
+        if probe_l0_seconds / SAMPLE_FRACTION[0] * SAMPLE_FRACTION[lvl] * n_steps <= budget_seconds:
+            return lvl
+    return 0
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warmup = args.steps, args.warmup
-    probe = cpu_sample(1, 0, max_level=0)          # ~2 s: init stage + level 0
-    lvl = 1 if probe * 3.0 * (steps + 1) < 150.0 else 0   # keep the whole run within a few minutes
-    t = cpu_sample(steps, min(warmup, 1), max_level=lvl)
+    probe = cpu_sample(1, 0, max_level=0)          # ~1 s: init stage + level 0
+    w = min(warmup, 1)
+    lvl = pick_sample_level(probe, steps + w, 300.0)   # keep the whole run within a few minutes
+    t = cpu_sample(steps, w, max_level=lvl)
     cores = _cpu_threads()
-    value = 1.0 / t
-    sample = ("per step: one full-size 9x640x480 fragment through occupancy initialisation + levels 0-1 (24^3, 48^3); "
-              "level 2 (96^3, ~95 % of the CPU time) skipped => upper bound on CPU fragments/s") if lvl == 1 else \
-             ("per step: one full-size 9x640x480 fragment through occupancy initialisation + level 0 only (configs[0]); "
-              "levels 1-2 skipped => upper bound on CPU fragments/s")
+    value = SAMPLE_FRACTION[lvl] / t
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": "fragments/s", "n_gpus": args.gpus,
-                      "steps": steps, "warmup": min(warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True,
+                      "steps": steps, "warmup": w, "ms_per_step": t * 1e3, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": WORKLOAD},
-                      "cpu_baseline": {"value": value, "unit": "fragments/s", "cores": cores, "kind": "port", "sample": sample,
-                                       "full_fragment_estimate": (value / FULL_OVER_SAMPLE) if lvl == 1 else None,
-                                       "full_fragment_note": FULL_NOTE, "host_cpus": os.cpu_count()},
+                      "cpu_baseline": {"value": value, "unit": "fragments/s", "cores": cores, "kind": "port", "sample": SAMPLE_TEXT[lvl],
+                                       "fragment_fraction_per_step": SAMPLE_FRACTION[lvl], "host_cpus": os.cpu_count()},
                       "e2e": {"value": value, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -552,12 +560,12 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not os.environ.get("EPRECON_BENCH_SKIP_CPU"):
-        t = cpu_sample(1, 0)
-        cpu_baseline = {"value": 1.0 / t, "unit": "fragments/s", "cores": _cpu_threads(), "host_cpus": os.cpu_count(), "kind": "port",
-                        "full_fragment_estimate": 1.0 / t / FULL_OVER_SAMPLE, "full_fragment_note": FULL_NOTE,
-                        "sample": "1 full-size fragment through occupancy initialisation + levels 0-1 (24^3, 48^3), "
-                                  f"{t:.1f} s of CPU work; level 2 (96^3, ~95 % of the CPU time) skipped => upper bound "
-                                  "on CPU fragments/s"}
+        probe = cpu_sample(1, 0, max_level=0)
+        lvl = pick_sample_level(probe, 1, 60.0)      # one step of ~20 s on 8-16 cores: the full fragment
+        t = cpu_sample(1, 0, max_level=lvl)
+        cpu_baseline = {"value": SAMPLE_FRACTION[lvl] / t, "unit": "fragments/s", "cores": _cpu_threads(), "host_cpus": os.cpu_count(),
+                        "kind": "port", "sample": SAMPLE_TEXT[lvl] + f"; {t:.1f} s of CPU work",
+                        "fragment_fraction_per_step": SAMPLE_FRACTION[lvl]}
 
     if rank == 0:
         print(json.dumps({
