@@ -462,15 +462,16 @@ def run_ours(args):
         for w in range(2):
             fragment(net0, resident[w], f"single_warm{w}")
         torch.cuda.synchronize()
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        evs[0].record()
         for k in range(K):
             fragment(net0, resident[k % n_copies], f"single{k}")
-        eb.record()
+            evs[k + 1].record()
         torch.cuda.synchronize()
-        single_ms = ea.elapsed_time(eb) / K
-        single = {"ms_per_fragment": single_ms, "fragments_per_s": 1e3 / single_ms,
-                  "note": "one fragment at a time on one stream (latency view of the same step)"}
+        per = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(K))
+        single_ms = per[len(per) // 2]      # median: this pass is host-bound (884 launches from one thread) and jittery
+        single = {"ms_per_fragment": single_ms, "fragments_per_s": 1e3 / single_ms, "ms_min": per[0], "ms_max": per[-1],
+                  "note": "one fragment at a time on one stream (latency view of the same step; median of K, host-bound)"}
         # launch count of one fragment on the shipped (native-executor) path
         # launch count of one steady-state fragment; cudaProfilerStart/Stop bracket exactly this fragment, so that
         # `ncu --profile-from-start off ... python bench.py` lists one fragment of this very command (profiles/README.md)
