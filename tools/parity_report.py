@@ -1,5 +1,7 @@
 """Per-stage parity report of the CUDA path against the CPU oracle on the small golden configuration, for every
-sparse-conv implementation (fp32 FFMA, tcgen05 3xTF32, tcgen05 TF32).  Prints one JSON line per implementation."""
+sparse-conv implementation (fp32 FFMA, tcgen05 3xTF32, tcgen05 TF32).  Prints one JSON line per implementation.
+`--full`: the same report on the FULL-size bench fragment (BASELINE configs[1]: 96^3, 9 x 640 x 480, ~210 k level-2
+candidates) -- the oracle takes ~12-22 s there, so this is the end-to-end parity check at the benchmarked size."""
 import json
 import os
 import sys
@@ -19,13 +21,21 @@ def rel(a, b):
 
 
 def main():
-    g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "neucon_small.npz"))
-    n_vox = tuple(int(v) for v in g["n_vox"])
-    cfg = synth.make_cfg(n_vox=n_vox)
-    cfg.THRESHOLDS = [float(v) for v in g["thresholds"]]
+    full = "--full" in sys.argv
+    if full:
+        # BASELINE configs[1] at its FULL size (96^3, 9 x 640 x 480, the bench fragment): the oracle needs ~12-22 s of CPU
+        cfg = synth.make_cfg()
+        cfg.THRESHOLDS = list(synth.BENCH_THRESHOLDS)
+        frag = dict(seed=1)
+    else:
+        g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "neucon_small.npz"))
+        n_vox = tuple(int(v) for v in g["n_vox"])
+        cfg = synth.make_cfg(n_vox=n_vox)
+        cfg.THRESHOLDS = [float(v) for v in g["thresholds"]]
+        frag = dict(seed=1, image_hw=(240, 320), n_vox=n_vox)
     net = NeuConNet(cfg)
     sd = synth.synthetic_state_dict(net, 1)
-    inputs, fa, fb = synth.make_fragment(seed=1, image_hw=(240, 320), n_vox=n_vox)
+    inputs, fa, fb = synth.make_fragment(**frag)
     ot = {}
     with torch.no_grad():
         oout = restate.neucon_forward(sd, cfg, fa, fb, inputs, restate.FusionState(), trace=ot)
@@ -39,7 +49,7 @@ def main():
         net.trace, net.teacher = {}, ot
         out, _ = net(fa_c, fb_c, cin, {})
         t = net.trace
-        rep = {"impl": impl, "init_occ": rel(t["init"]["occ"], ot["init"]["occ"])}
+        rep = {"impl": impl, "config": "full 96^3" if full else "golden 64^3", "init_occ": rel(t["init"]["occ"], ot["init"]["occ"])}
         for lv in range(3):
             a, b = t[f"l{lv}_pre_gru"], ot[f"l{lv}_pre_gru"]
             rep[f"l{lv}_coords_exact"] = bool(torch.equal(a["coords"].cpu(), b["coords"].int()))
