@@ -191,6 +191,7 @@ bn_finalize_kernel(const float* __restrict__ bn_partial, int nblk, int c, int m,
   const int col = blockIdx.x * 32 + tx;
   double s = 0.0, q = 0.0;
   if (col < c)
+#pragma unroll 4   // same sequential accumulation order, 8 independent loads in flight instead of 2 (latency-bound at 3000 tiles)
     for (int b = ty; b < nblk; b += 32) {
       s += (double)bn_partial[((size_t)b * 2 + 0) * c + col];
       q += (double)bn_partial[((size_t)b * 2 + 1) * c + col];
