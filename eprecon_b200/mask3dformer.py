@@ -101,9 +101,9 @@ class _Attention(nn.Module):
         v = F.linear(value_rows, self.in_proj_weight[2 * E:], self.in_proj_bias[2 * E:])
         return k.view(-1, h, E // h).transpose(0, 1), v.view(-1, h, E // h).transpose(0, 1)
 
-    def attend(self, query_rows, key_rows, value_rows, blocked=None):
+    def attend(self, query_rows, key_rows, value_rows, blocked=None, fused=False):
         E, h = self.embed_dim, self.num_heads
-        if FUSED_ATTENTION and E // h == 6 and h <= 8 and query_rows.shape[0] <= 96 and key_rows.shape[0] > query_rows.shape[0]:
+        if fused and FUSED_ATTENTION and E // h == 6 and h <= 8 and query_rows.shape[0] <= 96:
             # cross-attention over the voxel keys: one fused pass (score -> mask -> online softmax -> weighted sum,
             # csrc/attention.cu) instead of [heads, Q, N] score tensors and two batched GEMMs with a dimension of 6
             q = F.linear(query_rows, self.in_proj_weight[:E], self.in_proj_bias[:E])
@@ -144,7 +144,7 @@ class CrossAttentionLayer(nn.Module):
     def forward(self, tgt, memory, memory_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None):
         q = tgt if query_pos is None else tgt + query_pos
         k = memory if pos is None else memory + pos
-        return self.norm(tgt + self.multihead_attn.attend(q, k, memory, memory_mask))
+        return self.norm(tgt + self.multihead_attn.attend(q, k, memory, memory_mask, fused=True))
 
 
 class FFNLayer(nn.Module):
@@ -249,7 +249,7 @@ class MultiScaleMaskedTransformerDecoder(nn.Module):
             l = j % self.num_feature_levels
             blocked = blocked & ~blocked.all(dim=1, keepdim=True)                     # fully blocked query -> attends everywhere
             ca = self.transformer_cross_attention_layers[j]
-            out = ca.norm(out + ca.multihead_attn.attend(out + qpos, keys[l], src[l], blocked))
+            out = ca.norm(out + ca.multihead_attn.attend(out + qpos, keys[l], src[l], blocked, fused=True))
             out = self.transformer_self_attention_layers[j](out, query_pos=qpos)
             out = self.transformer_ffn_layers[j](out)
             logits, masks, blocked = self.forward_prediction_heads(out, mask_rows, index[(j + 1) % self.num_feature_levels])
