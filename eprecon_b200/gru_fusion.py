@@ -339,7 +339,9 @@ class GRUFusion(nn.Module):
             return outputs
         if not coords_all:
             return None, None, None, None
-        cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs)) if True else None
+        def cat(xs):
+            return xs[0] if len(xs) == 1 else torch.cat(xs)
+
         coords_out = cat(coords_all)
         if not self.return_int32:
             coords_out = coords_out.long()
