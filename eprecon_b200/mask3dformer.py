@@ -69,17 +69,19 @@ class PositionEmbeddingCoordsSine(nn.Module):
 
 
 class MLP(nn.Module):
+    """Linear stack with ReLU between the layers (state-dict names `layers.N.{weight,bias}` as in the reference)."""
+
     def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
         super().__init__()
+        widths = [input_dim] + [hidden_dim] * (num_layers - 1) + [output_dim]
         self.num_layers = num_layers
-        h = [hidden_dim] * (num_layers - 1)
-        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+        self.layers = nn.ModuleList([nn.Linear(widths[i], widths[i + 1]) for i in range(num_layers)])
 
     def forward(self, x):
-        for i, layer in enumerate(self.layers):
-            x = layer(x)
-            if i < self.num_layers - 1:
-                x = F.relu(x)
+        last = self.num_layers - 1
+        for i in range(self.num_layers):
+            x = self.layers[i](x)
+            x = x if i == last else F.relu(x)
         return x
 
 
