@@ -19,7 +19,7 @@ __device__ __forceinline__ void table_insert(uint64_t* __restrict__ tk, int* __r
   while (true) {
     unsigned long long prev = atomicCAS((unsigned long long*)&tk[slot], (unsigned long long)EP_HASH_EMPTY,
                                         (unsigned long long)key);
-    if (prev == EP_HASH_EMPTY) { tv[slot] = val; return; }
+    if (prev == EP_HASH_EMPTY) { atomicMin(&tv[slot], val); return; }   // tv is pre-set to INT_MAX: a racing duplicate's smaller row survives
     if (prev == key) { atomicMin(&tv[slot], val); return; }  // duplicate key: first (lowest) row wins
     slot = (slot + 1) & mask;
   }

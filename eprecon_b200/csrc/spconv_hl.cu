@@ -1,0 +1,485 @@
+// Sparse 3-D convolution, operand path rebuilt around the TMA engine ("hl" = half-pair operands).
+//
+//     out[j, :] = bias + sum_k W[k]^T . in[nbr[j, k], :]           (same contract as ep_spconv_fwd / ep_spconv_tc_fwd)
+//
+// What changed against csrc/spconv_tc.cu (round-1 kernel: 8 producer warps LDG -> cvt -> STS an fp32 operand that was
+// split into tf32 hi/lo planes on the fly; L1TEX-bound at 81 %, tensor pipe 8.6 %, profiles/r01_spconv_tc_v7_*):
+//   * activations reach this kernel PRE-SPLIT: every fp32 value x is stored by its producer as a pair of halfs
+//     (h, l) with h = fp16(x), l = fp16((x - h) * 2^11) -- 22 significant bits, the same budget as the 3xTF32 split,
+//     in 4 bytes per value instead of 8.  Rows are laid out in 32-channel slabs of 128 bytes [h0..h31 | l0..l31], which
+//     is exactly one SWIZZLE_128B row of a K-major UMMA operand.
+//   * no thread touches an operand: one warp issues 32 `cp.async.bulk.tensor.2d.tile::gather4` per pipeline stage (4
+//     neighbour rows each, row indices straight from the staged neighbour table; a missing neighbour is an
+//     out-of-bounds row, which the TMA unit zero-fills) and one tiled TMA load for the matching weight slab; both land
+//     in shared memory in the canonical swizzled layout and complete on the stage's mbarrier (complete_tx).
+//   * one thread issues tcgen05.mma.kind::f16 (M = 128, N = padded cout, K = 16): per stage and 16-channel step the
+//     products h.h (rotating over three TMEM accumulators: the tensor core truncates when it chains an accumulator, see
+//     spconv_tc.cu), l.h and h.l (a fourth accumulator, scaled by 2^-11 in the epilogue).
+//   * 4 epilogue warps: tcgen05.ld, sum the accumulators in fp32, bias, store, per-CTA BatchNorm partial sums.
+// SASS evidence: UTMALDG (gather4 + tile), UTCHMMA, UTCBAR, LDTM; no LDG/STS on the operand path.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace eptc;
+
+constexpr int HTM = 128;                   // output rows per CTA (UMMA M)
+constexpr int H_THREADS = 192;             // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int A_STAGE = HTM * 128;         // bytes of one gathered A slab (128 rows x [32 h | 32 l] halfs)
+constexpr int NBS = 132;                   // ints per offset in the staged neighbour table (16-byte aligned rows)
+constexpr int MAX_STAGES = 8;
+
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                   // leading byte offset: unused for swizzled K-major operands
+  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset: one 8-row x 128-byte swizzle atom
+  d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_gather4(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int col, int r0, int r1,
+                                            int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3),
+        "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_tile2d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// mbarrier wait that cannot hang the device: a barrier that does not flip within ~2 s is a protocol bug -> trap (the
+// launch fails with an error instead of wedging the GPU).
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__global__ void __launch_bounds__(H_THREADS)
+spconv_hl_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const int* __restrict__ nbr, int K, int nslab, int npad, int nt, int tmem_cols, int nstage, int cout,
+                 int neg_row /* row index used for "no neighbour": any out-of-bounds row */,
+                 const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m_out,
+                 float* __restrict__ bn_partial, int bn_rows, int splits, float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // SWIZZLE_128B atoms: 1024-byte aligned
+  const int b_stage = nt * 128;
+  const int stage_bytes = A_STAGE + b_stage;
+  int* s_nbr = reinterpret_cast<int*>(smem + (size_t)nstage * stage_bytes);       // [K][NBS]
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
+  __shared__ uint64_t all_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_mask, s_used;
+  __shared__ float s_red[8][128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * HTM;
+  const int col0 = blockIdx.y * nt;
+  const int kb = (int)(((long long)blockIdx.z * K) / splits), ke = (int)(((long long)(blockIdx.z + 1) * K) / splits);
+
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&all_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_mask = 0;
+    s_used = 0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // neighbour table of the tile, transposed to [k][row]; rows past m_out read as "no neighbour"
+  {
+    constexpr int PU = 6;
+    const int total = HTM * K;
+    const long long base = (long long)row0 * K, lim = (long long)m_out * K;
+    unsigned mine = 0;
+    for (int e0 = 0; e0 < total; e0 += H_THREADS * PU) {
+      int v[PU];
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int e = e0 + u * H_THREADS + tid;
+        v[u] = -1;
+        if (e < total && base + e < lim) v[u] = nbr ? __ldg(nbr + base + e) : row0 + e;   // no table: K == 1, identity
+      }
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int e = e0 + u * H_THREADS + tid;
+        if (e < total) {
+          const int r = e / K, kq = e - r * K;
+          s_nbr[kq * NBS + r] = v[u] >= 0 ? v[u] : neg_row;
+          if (v[u] >= 0 && kq >= kb && kq < ke) mine |= 1u << kq;
+        }
+      }
+    }
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if (lane == 0 && mine) atomicOr(&s_mask, (int)mine);
+  }
+  __syncthreads();
+  const unsigned kmask = (unsigned)s_mask;
+  const uint32_t tmem_d = tmem_base_s;
+  const int T = __popc(kmask) * nslab;      // pipeline stages of this CTA
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer: 32 gather4 + 1 weight tile per stage
+    int stage = 0, round = 0;
+    unsigned rem = kmask;
+    while (rem) {
+      const int k = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const int4 rows = *reinterpret_cast<const int4*>(&s_nbr[k * NBS + 4 * lane]);
+      for (int c = 0; c < nslab; ++c) {
+        if (round > 0) mbar_wait_b(&empty_bar[stage], (round - 1) & 1);
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(A_STAGE + b_stage));
+          tma_tile2d(&tm_b, &full_bar[stage], sa + A_STAGE, 0, (k * nslab + c) * npad + col0);
+        }
+        __syncwarp();
+        tma_gather4(&tm_a, &full_bar[stage], sa + lane * 512, c * 64, rows.x, rows.y, rows.z, rows.w);
+        if (++stage == nstage) { stage = 0; ++round; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(HTM >> 4) << 24);   // f16 x f16 -> f32
+      uint32_t used = 0;
+      int stage = 0, round = 0;
+      for (int t = 0; t < T; ++t) {
+        mbar_wait_b(&full_bar[stage], round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + A_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint64_t dah = umma_desc_sw128(sa + kk * 32), dal = umma_desc_sw128(sa + 64 + kk * 32);
+          const uint64_t dbh = umma_desc_sw128(sb + kk * 32), dbl = umma_desc_sw128(sb + 64 + kk * 32);
+          const int am = (t * 2 + kk) % 3;
+          umma_f16(tmem_d + am * nt, dah, dbh, idesc, (used >> am) & 1u);
+          used |= 1u << am;
+          umma_f16(tmem_d + 3 * nt, dal, dbh, idesc, (used >> 3) & 1u);
+          used |= 1u << 3;
+          umma_f16(tmem_d + 3 * nt, dah, dbl, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == nstage) { stage = 0; ++round; }
+      }
+      umma_commit(&all_done);
+      s_used = (int)used;
+    }
+  }
+  __syncthreads();
+  if (warp >= 2) {
+    // ------------------------------------------------------------- epilogue (warps 2..5 own TMEM lanes 32 * (warp & 3))
+    if (T > 0) mbar_wait_b(&all_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t used = (uint32_t)s_used;
+    const int q = warp & 3;
+    const int row = row0 + q * 32 + lane;
+    for (int cb = 0; cb < nt; cb += 16) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      if (T > 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          if ((used >> a) & 1u) {
+            float t16[16];
+            tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * nt + cb), t16);
+            const float sc = a == 3 ? (1.f / 2048.f) : 1.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(t16[i], sc, v[i]);
+          }
+        }
+      }
+      if (splits > 1) {   // raw partial sums; bias / statistics are applied by the split-K reduce
+        if (row < m_out) {
+          float4* dst = reinterpret_cast<float4*>(partial + ((size_t)blockIdx.z * m_out + row) * npad + col0 + cb);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        continue;
+      }
+      float s[16], sq[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int col = col0 + cb + i;
+        const float val = v[i] + ((bias && col < cout) ? bias[col] : 0.f);
+        const bool ok = row < m_out && col < cout;
+        if (ok) out[(size_t)row * ld_out + col] = val;
+        s[i] = ok ? val : 0.f;
+        sq[i] = ok ? val * val : 0.f;
+      }
+      if (bn_partial) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], d);
+            sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], d);
+          }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { s_red[q][cb + i] = s[i]; s_red[4 + q][cb + i] = sq[i]; }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (bn_partial && splits == 1 && tid < nt) {
+    const int col = col0 + tid;
+    if (col < cout) {
+      const float s = (s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]);
+      const float sq = (s_red[4][tid] + s_red[5][tid]) + (s_red[6][tid] + s_red[7][tid]);
+      const int r0 = 2 * blockIdx.x;   // bn_partial is sized for 64-row tiles: fill entry 2*bx, zero 2*bx+1
+      bn_partial[((size_t)r0 * 2 + 0) * cout + col] = s;
+      bn_partial[((size_t)r0 * 2 + 1) * cout + col] = sq;
+      if (r0 + 1 < bn_rows) {
+        bn_partial[((size_t)(r0 + 1) * 2 + 0) * cout + col] = 0.f;
+        bn_partial[((size_t)(r0 + 1) * 2 + 1) * cout + col] = 0.f;
+      }
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols));
+  }
+}
+
+// fp32 rows [m, ld] (c valid columns) -> half-pair rows [m][nslab][32 h | 32 l].  One thread = 8 channels of one row.
+__global__ void __launch_bounds__(256)
+hl_split_kernel(const float* __restrict__ src, int ld, int c, long long m, int nslab, uint4* __restrict__ dst,
+                int* __restrict__ overflow) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m * nslab * 4) return;
+  const int oct = (int)(t & 3);
+  const long long rs = t >> 2;
+  const int slab = (int)(rs % nslab);
+  const long long row = rs / nslab;
+  const int ch0 = slab * 32 + oct * 8;
+  float v[8];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int ch = ch0 + 4 * g;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ch < c) f = __ldg(reinterpret_cast<const float4*>(src + row * ld + ch));   // ld % 4 == 0: whole quads are in-row
+    v[4 * g + 0] = f.x;
+    v[4 * g + 1] = ch + 1 < c ? f.y : 0.f;
+    v[4 * g + 2] = ch + 2 < c ? f.z : 0.f;
+    v[4 * g + 3] = ch + 3 < c ? f.w : 0.f;
+  }
+  __half h[8], l[8];
+  bool big = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __float2half_rn(v[i]);
+    l[i] = __float2half_rn((v[i] - __half2float(h[i])) * 2048.f);
+    big |= fabsf(v[i]) > 65000.f;
+  }
+  if (big && overflow) atomicOr(overflow, 1);
+  uint4* d = dst + (row * nslab + slab) * 8;     // 8 x 16 bytes per slab row
+  d[oct] = *reinterpret_cast<const uint4*>(h);
+  d[4 + oct] = *reinterpret_cast<const uint4*>(l);
+}
+
+// debugging aid: one warp gathers 128 rows of slab `slab` with 32 gather4 and dumps the raw 16 KB of shared memory
+__global__ void __launch_bounds__(32)
+hl_probe_gather4_kernel(const __grid_constant__ CUtensorMap tm_a, const int* __restrict__ rows128, int slab,
+                        uint4* __restrict__ out, int* __restrict__ status) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = lane; i < A_STAGE / 16; i += 32) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive_expect_tx(&bar, A_STAGE);
+  __syncwarp();
+  const int4 r = reinterpret_cast<const int4*>(rows128)[lane];
+  tma_gather4(&tm_a, &bar, smem + lane * 512, slab * 64, r.x, r.y, r.z, r.w);
+  // bounded wait: report a timeout instead of trapping
+  const uint32_t addr = smem_u32(&bar);
+  const long long t0 = clock64();
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(0u) : "memory");
+    if (!done && clock64() - t0 > 400000000LL) break;
+  }
+  if (lane == 0) *status = done ? 1 : -1;
+  __syncwarp();
+  for (int i = lane; i < A_STAGE / 16; i += 32) out[i] = reinterpret_cast<const uint4*>(smem)[i];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// 2-D map over rows of `row_halfs` halfs (pitch = row_halfs * 2 bytes), box = 64 halfs x box_rows, SWIZZLE_128B
+bool make_map(CUtensorMap* map, const void* base, uint64_t row_halfs, uint64_t rows, uint32_t box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {row_halfs, rows};
+  const cuuint64_t strides[1] = {row_halfs * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+int hl_splits(int64_t m_out, int npad, int K) {
+  const int nt = npad > 128 ? 128 : npad;
+  const long long ctas = (long long)ep_div_up(m_out, HTM) * (npad / nt);
+  if (K < 2 || ctas * 2 > EP_NUM_SMS) return 1;
+  long long s = EP_NUM_SMS / ctas;
+  if (s > K) s = K;
+  return s < 2 ? 1 : (int)s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ep_hl_slabs(int c) { return (c + 31) / 32; }
+
+// src f32 [m, ld_src] (c valid columns, ld_src % 4 == 0) -> dst half pairs [m][ep_hl_slabs(c)][64] (128 bytes per slab).
+// overflow (optional): set to 1 when a value is outside the half range (|x| > 65000).
+int ep_hl_split_rows(const float* src, int ld_src, int c, int64_t m, uint16_t* dst, int32_t* overflow, cudaStream_t stream) {
+  if (m <= 0 || c < 1 || ld_src % 4 != 0 || ((c + 3) / 4 * 4) > ld_src) return EP_ERR_ARG;
+  if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return EP_ERR_ARG;
+  const int nslab = (c + 31) / 32;
+  const long long total = (long long)m * nslab * 4;
+  hl_split_kernel<<<ep_div_up(total, 256), 256, 0, stream>>>(src, ld_src, c, (long long)m, nslab, reinterpret_cast<uint4*>(dst),
+                                                             overflow);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
+size_t ep_spconv_hl_workspace_bytes(int64_t m_out, int npad, int K) {
+  const int s = hl_splits(m_out, npad, K);
+  return s > 1 ? (size_t)s * (size_t)m_out * (size_t)npad * sizeof(float) : 0;
+}
+
+// in_hl: half-pair rows of the m_in input rows (ep_hl_split_rows); w_hl: half-pair weights [K][nslab][npad][64]
+// (w_hl[k][s][n][j] = fp16(W[k][32 s + j][n]), [..][32 + j] = fp16 of the remainder * 2^11; zero padded), npad = cout
+// rounded up to a multiple of 16 (of 128 when larger).  neg_row_mode 0: a missing neighbour is gathered as row m_in (first
+// out-of-bounds row), 1: as row -1.  Other arguments as ep_spconv_tc_fwd.
+int ep_spconv_hl_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t* nbr, int K, const uint16_t* w_hl, int npad,
+                     int cout, const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, void* workspace,
+                     size_t workspace_bytes, int neg_row_mode, cudaStream_t stream) {
+  if (m_out <= 0 || m_in <= 0 || m_in > 0x7ffffff0LL || cin < 1 || cout < 1 || K < 1 || npad % 16 != 0 || npad < cout)
+    return EP_ERR_ARG;
+  if (!nbr && K != 1) return EP_ERR_ARG;
+  if (K > 27) return EP_ERR_UNSUPPORTED;
+  if (((uintptr_t)in_hl & 15) || ((uintptr_t)w_hl & 15)) return EP_ERR_ARG;
+  int nt = npad;
+  if (npad > 128) {
+    if (npad % 128 != 0) return EP_ERR_ARG;
+    nt = 128;
+  }
+  const int nslab = (cin + 31) / 32;
+  const int tmem_cols = pow2_cols(4 * nt);
+  if (tmem_cols > 512) return EP_ERR_UNSUPPORTED;
+  CUtensorMap tm_a, tm_b;
+  if (!make_map(&tm_a, in_hl, (uint64_t)nslab * 64, (uint64_t)m_in, 1)) return EP_ERR_CUDA;
+  if (!make_map(&tm_b, w_hl, 64, (uint64_t)K * nslab * npad, (uint32_t)nt)) return EP_ERR_CUDA;
+  const int stage_bytes = A_STAGE + nt * 128;
+  // TMEM decides how many CTAs share an SM (512 columns): give each the deepest ring its share of shared memory allows
+  const int ctas_per_sm = 512 / tmem_cols >= 2 ? 2 : 1;
+  const int budget = (ctas_per_sm == 2 ? 110 : 220) * 1024 - K * NBS * 4 - 1024;
+  int nstage = budget / stage_bytes;
+  if (nstage > MAX_STAGES) nstage = MAX_STAGES;
+  if (nstage < 2) return EP_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)nstage * stage_bytes + (size_t)K * NBS * sizeof(int) + 1024;
+  static const cudaError_t attr = cudaFuncSetAttribute(spconv_hl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  if (attr != cudaSuccess) return EP_ERR_CUDA;
+  const int splits = hl_splits(m_out, npad, K);
+  if (splits > 1 && workspace_bytes < ep_spconv_hl_workspace_bytes(m_out, npad, K)) return EP_ERR_WORKSPACE;
+  float* partial = splits > 1 ? (float*)workspace : nullptr;
+  dim3 grid(ep_div_up(m_out, HTM), npad / nt, splits);
+  const int bn_rows = ep_div_up(m_out, 64);
+  const int neg_row = neg_row_mode == 1 ? -1 : (int)m_in;
+  spconv_hl_kernel<<<grid, H_THREADS, smem, stream>>>(tm_a, tm_b, nbr, K, nslab, npad, nt, tmem_cols, nstage, cout, neg_row, bias,
+                                                      out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial);
+  if (splits > 1) {
+    const int s = ep_internal_splitk_reduce(partial, splits, (int)m_out, npad, cout, bias, out, ld_out, bn_partial, stream);
+    if (s != EP_OK) return s;
+  }
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
+// Debug entry: gathers the 128 rows `rows128` (device int32[128]; any value, out-of-range rows must read as zeros) of slab
+// `slab` of in_hl [m_in][nslab][64] with 32 gather4 and returns the raw shared-memory image (16 KB) + status (1 ok, -1 timeout).
+int ep_hl_probe_gather4(const uint16_t* in_hl, int64_t m_in, int nslab, const int32_t* rows128, int slab, void* out16k,
+                        int32_t* status, cudaStream_t stream) {
+  CUtensorMap tm_a;
+  if (!make_map(&tm_a, in_hl, (uint64_t)nslab * 64, (uint64_t)m_in, 1)) return EP_ERR_CUDA;
+  hl_probe_gather4_kernel<<<1, 32, A_STAGE + 1024, stream>>>(tm_a, rows128, slab, reinterpret_cast<uint4*>(out16k), status);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
+}  // extern "C"

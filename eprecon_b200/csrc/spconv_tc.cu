@@ -392,6 +392,15 @@ inline int pow2_cols(int n) {
 
 }  // namespace
 
+// shared with csrc/spconv_hl.cu: fixed-order reduction of split-K partial sums (+ bias, + BatchNorm partial statistics)
+int ep_internal_splitk_reduce(const float* partial, int splits, int m_out, int npad, int cout, const float* bias, float* out,
+                              int ld_out, float* bn_partial, cudaStream_t stream) {
+  splitk_reduce_kernel<<<dim3(ep_div_up(m_out, 64), ep_div_up(cout, 128)), 256, 0, stream>>>(partial, splits, m_out, npad, cout, bias,
+                                                                                            out, ld_out, bn_partial);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
 extern "C" {
 
 // Weights must be pre-arranged as float[K][nq][npad][4] (w[k][q][n][i] = W[k][4q+i][n], zero padded; nq = ceil(cin/4)

@@ -2,6 +2,10 @@
 #pragma once
 #include "common.cuh"
 
+// csrc/spconv_tc.cu
+int ep_internal_splitk_reduce(const float* partial, int splits, int m_out, int npad, int cout, const float* bias, float* out,
+                              int ld_out, float* bn_partial, cudaStream_t stream);
+
 namespace eptc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

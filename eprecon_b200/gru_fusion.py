@@ -305,9 +305,9 @@ class GRUFusion(nn.Module):
             if self.direct_substitude and panoptic_infos is not None:
                 # gru_fusion.py:352-363: the fragment's segment ids at the union sites (0 where only the scene has a voxel)
                 info = panoptic_infos[i]
+                # panoptic_seg is already per fragment (NeuConNet.panoptic_decode emits one per batch entry over that entry's
+                # voxels, rows aligned with this entry's coords; the reference pairs it directly, gru_fusion.py:355)
                 seg = info["panoptic_seg"][0].to(torch.int32)
-                if batch_size > 1:
-                    seg = seg[sel]
                 info["panoptic_seg"][0] = torch.where(row_a >= 0, seg[row_a.clamp_min(0).long()], torch.zeros((), dtype=torch.int32, device=dev))
                 new_inst, new_sem = self.panoptic_fusion(scale=scale, global_valid=valid, relative_origin=rel, panoptic_info=info,
                                                          current_coords=upd[:, 1:], row_b=row_b)

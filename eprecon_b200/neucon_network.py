@@ -116,6 +116,11 @@ class NeuConNet(nn.Module):
                 only_train_occ=False, init_overlap_count=0):
         if only_train_init or only_train_occ:
             raise NotImplementedError("training-only modes are outside the B200 inference path")
+        if not self.training:
+            # every BatchNorm on this path normalises with the statistics of the current fragment, as the reference does when it
+            # evaluates in train() mode (main.py:357); running statistics are neither kept nor applied, so eval() is refused
+            # rather than silently giving a third behaviour
+            raise RuntimeError("eprecon_b200.NeuConNet runs in train() mode only (batch-statistics BatchNorm, reference main.py:357)")
         cfg = self.cfg
         bs = features[0][0].shape[0]
         dev = features[0][0].device

@@ -310,6 +310,44 @@ def _umma_weights(W, cout, prec):
     return hit[0], hit[1], hit[2]
 
 
+_HL_CACHE = {}
+HL_NEG_ROW_MODE = int(os.environ.get("EPRECON_HL_NEG", "0"))
+
+
+def _hl_weights(W, cout):
+    """FFMA-layout weights [K, cin, ceil4(cout)] -> (w_hl uint16-as-half [K][nslab][npad][64], npad): per 32-channel slab
+    and output channel the 32 halfs h = fp16(w) followed by the 32 halfs fp16((w - h) * 2^11) (csrc/spconv_hl.cu)."""
+    key = (W.data_ptr(), W._version, tuple(W.shape))
+    hit = _HL_CACHE.get(key)
+    if hit is None:
+        K, cin, _ = W.shape
+        npad = (cout + 15) // 16 * 16
+        if npad > 128:
+            npad = (cout + 127) // 128 * 128
+        nslab = (cin + 31) // 32
+        wp = torch.zeros((K, nslab * 32, npad), dtype=torch.float32, device=W.device)
+        wp[:, :cin, :cout] = W[:, :, :cout]
+        h = wp.half()
+        lo = ((wp - h.float()) * 2048.0).half()
+        h4 = h.view(K, nslab, 32, npad).permute(0, 1, 3, 2)
+        l4 = lo.view(K, nslab, 32, npad).permute(0, 1, 3, 2)
+        w_hl = torch.cat([h4, l4], dim=3).contiguous()
+        if len(_HL_CACHE) > 4096:
+            _HL_CACHE.clear()
+        hit = _HL_CACHE[key] = (w_hl, npad, W)
+    return hit[0], hit[1]
+
+
+def hl_split(x, c, overflow=None):
+    """fp32 rows [m, ld] -> half-pair rows [m, nslab*64] (fp16 storage) for ep_spconv_hl_fwd."""
+    m = x.shape[0]
+    nslab = (c + 31) // 32
+    out = torch.empty((m, nslab * 64), dtype=torch.float16, device=x.device)
+    _lib.check(_L().ep_hl_split_rows(x.data_ptr(), x.stride(0), c, m, out.data_ptr(), _ptr(overflow), stream_ptr()),
+               "ep_hl_split_rows")
+    return out
+
+
 def spconv(x, cin, nbr, W, cout, bias=None, m_out=None, want_stats=False, out=None, out_col=0):
     """out[j,:cout] = bias + sum_k W[k]^T x[nbr[j,k], :cin].  x [*, ld]; W [K, cin, ceil4(cout)] prepared by the
     module.  Returns (out [m_out, ceil4(cout)] or view into `out`, bn_partial or None)."""
@@ -333,6 +371,14 @@ def spconv(x, cin, nbr, W, cout, bias=None, m_out=None, want_stats=False, out=No
         _lib.check(L.ep_spconv_fwd(x.data_ptr(), x.stride(0), cin, _ptr(nbr), K, W.data_ptr(), W.shape[2], cout,
                                    _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
                                    stream_ptr()), "ep_spconv_fwd")
+    elif SPCONV_IMPL == "hl":
+        w_hl, npad = _hl_weights(W, cout)
+        x_hl = hl_split(x, cin)
+        wsb = L.ep_spconv_hl_workspace_bytes(m_out, npad, K)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
+        _lib.check(L.ep_spconv_hl_fwd(x_hl.data_ptr(), x.shape[0], cin, _ptr(nbr), K, w_hl.data_ptr(), npad, cout,
+                                      _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
+                                      _ptr(ws), wsb, HL_NEG_ROW_MODE, stream_ptr()), "ep_spconv_hl_fwd")
     else:
         prec = 3 if SPCONV_IMPL == "tf32x3" else 1
         w_hi, w_lo, npad = _umma_weights(W, cout, prec)

@@ -24,15 +24,31 @@ def replicate(net):
     state and caches."""
     from .neucon_network import NeuConNet
     rep = NeuConNet(net.cfg)
-    src_p, src_b = dict(net.named_parameters()), dict(net.named_buffers())
-    for name, p in rep.named_parameters():
-        p.data = src_p[name].data
-    for name, b in rep.named_buffers():
-        b.data = src_b[name].data
+    # share the Parameter / buffer OBJECTS, not just their storage: every prepared-weight cache is keyed on
+    # (data_ptr, _version), and a private Parameter would keep its own version counter -- a later load_state_dict or
+    # optimizer step on `net` would then leave the replicas computing with stale weight slabs.
+    src_mods = dict(net.named_modules())
+    for mname, mod in rep.named_modules():
+        src = src_mods[mname]
+        for pname in list(mod._parameters):
+            mod._parameters[pname] = src._parameters[pname]
+        for bname in list(mod._buffers):
+            mod._buffers[bname] = src._buffers[bname]
     rep.train(net.training)
     rep.with_panoptic_features = net.with_panoptic_features
     rep.with_panoptic = net.with_panoptic
     return rep
+
+
+def _flatten(x):
+    if isinstance(x, dict):
+        for v in x.values():
+            yield from _flatten(v)
+    elif isinstance(x, (list, tuple)):
+        for v in x:
+            yield from _flatten(v)
+    else:
+        yield x
 
 
 class _Future:
@@ -82,10 +98,23 @@ class FragmentStreams:
             except BaseException as e:  # surfaced by Future.result() on the submitting thread
                 fut.set(exc=e)
 
-    def submit(self, slot, fn):
-        """Run fn(net_replica, cuda_stream) on worker `slot` (its stream is current); returns a future."""
+    def submit(self, slot, fn, inputs=None):
+        """Run fn(net_replica, cuda_stream) on worker `slot` (its stream is current); returns a future.  The worker's stream
+        first waits for everything the SUBMITTING thread's current stream has enqueued so far (the producers of the
+        fragment's tensors, e.g. a 2-D backbone); `inputs` (optional iterable of tensors allocated on other streams) are
+        recorded on the worker stream so the caching allocator cannot recycle them while it still reads them."""
         fut = _Future()
-        self._queues[slot].put((fn, fut))
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        stream = self.streams[slot]
+        tensors = [t for t in _flatten(inputs) if torch.is_tensor(t) and t.is_cuda] if inputs is not None else []
+
+        def job(net, st):
+            st.wait_event(ev)
+            for t in tensors:
+                t.record_stream(st)
+            return fn(net, st)
+        self._queues[slot].put((job, fut))
         return fut
 
     def warm(self, fn):
@@ -106,7 +135,7 @@ class FragmentStreams:
                 stream.synchronize()
                 return res
             return run
-        futs = [self.submit(j % s, job(f)) for j, f in enumerate(fragments)]
+        futs = [self.submit(j % s, job(f), inputs=f[:3]) for j, f in enumerate(fragments)]
         return [f.result() for f in futs]
 
     def close(self):

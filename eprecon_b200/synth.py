@@ -207,3 +207,8 @@ def synthetic_state_dict(module, seed=1):
 # (4.1 k / 26 k / 105 k occupied voxels; /tmp calibration run recorded in DESIGN.md).  Random weights would
 # otherwise leave ~6 % occupied and trip the reference's `< 500 voxels` early return.
 BENCH_THRESHOLDS = [-1.666, -0.471, -0.39]
+
+# Same idea for BASELINE configs[4] (18 views, 960x720, 128^3): with the 96^3 thresholds the level-2 occupancy (174 k of
+# 373 k candidates) would trip the shipped 1.5 x 120 000 cap (config/test.yaml:29; neucon_network.py:469-475).  Calibrated
+# on the CPU oracle (seed-1 weights / fragment): 6 968 / 46 649 / 109 439 occupied voxels, all inside the shipped caps.
+HIGHRES_THRESHOLDS = [-1.666, -0.471, -0.17]

@@ -115,6 +115,19 @@ size_t ep_spconv_tc_workspace_bytes(int64_t m_out, int npad, int K);
 int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, int K, const float* w_hi,
                      const float* w_lo, int npad, int cout, const float* bias, float* out, int ld_out, int64_t m_out,
                      float* bn_partial, int prec, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* TMA-gather variant (csrc/spconv_hl.cu): operands are PRE-SPLIT half pairs -- x = h + l * 2^-11, h = fp16(x), 22 significant
+ * bits like 3xTF32 at half the bytes -- stored in 32-channel slabs of 128 bytes [32 h | 32 l], the SWIZZLE_128B row of a K-major
+ * tcgen05 operand; rows are fetched by cp.async.bulk.tensor tile::gather4 straight from the neighbour table (no LDG/STS on
+ * the operand path), tcgen05.mma kind::f16 with fp32 accumulators in TMEM.  in_hl [m_in][nslab][64] halfs, nslab = ceil(cin / 32);
+ * w_hl [K][nslab][npad][64] halfs; npad = cout rounded up to 16 (to 128 when larger). */
+int ep_hl_slabs(int c);
+int ep_hl_split_rows(const float* src, int ld_src, int c, int64_t m, uint16_t* dst, int32_t* overflow, cudaStream_t stream);
+size_t ep_spconv_hl_workspace_bytes(int64_t m_out, int npad, int K);
+int ep_spconv_hl_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t* nbr, int K, const uint16_t* w_hl, int npad,
+                     int cout, const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, void* workspace,
+                     size_t workspace_bytes, int neg_row_mode, cudaStream_t stream);
+int ep_hl_probe_gather4(const uint16_t* in_hl, int64_t m_in, int nslab, const int32_t* rows128, int slab, void* out16k,
+                        int32_t* status, cudaStream_t stream);
 int ep_colstats(const float* x, int ld, int64_t m, int c, float* bn_partial, cudaStream_t stream);
 int ep_bn_finalize(const float* bn_partial, int num_row_tiles, int c, int64_t m, float eps, const float* gamma,
                    const float* beta, float* scale_shift, float* mean_var, cudaStream_t stream);

@@ -158,6 +158,35 @@ def test_direct_substitute_panoptic_fusion_matches_reference(cuda_lib):
         assert np.array_equal(np.bincount(outputs["scene_semantic"][-1].cpu().long().flatten().numpy()), g[f"f{frag}_scene_semantic_hist"])
 
 
+def test_direct_substitute_panoptic_fusion_batch_of_two(cuda_lib):
+    """bs = 2: fragments 0 and 1 of one scene as ONE batched call.  The reference loops over the batch entries against the
+    same global state (models/gru_fusion.py:274-369) and pairs panoptic_infos[i]['panoptic_seg'][0] row for row with entry
+    i's voxels (:355), so the state after the call equals the fixture's state after fragment 1."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from make_golden_panoptic_fusion import N_VOX, fusion_inputs
+    from eprecon_b200.gru_fusion import GRUFusion
+    g = np.load(os.path.join(HERE, "golden", "panoptic_fusion_small.npz"))
+    cfg = synth.make_cfg(n_vox=N_VOX)
+    fuse = GRUFusion(cfg, direct_substitute=True, trianing=False)
+    parts = [fusion_inputs(f) for f in (0, 1)]
+    cin = {}
+    for k in ("proj_matrices", "vol_origin_partial", "vol_origin", "world_to_aligned_camera"):
+        cin[k] = torch.cat([p[0][k] for p in parts]).cuda()
+    cin["scene"] = [p[0]["scene"][0] for p in parts]
+    cin["fragment"] = [p[0]["fragment"][0] for p in parts]
+    coords = torch.cat([torch.cat([torch.full((len(p[1]), 1), b, dtype=torch.long), p[1][:, 1:]], 1) for b, p in enumerate(parts)])
+    tsdf = torch.cat([p[2] for p in parts])
+    infos = [{"panoptic_seg": [p[3]["panoptic_seg"][0].cuda(), p[3]["panoptic_seg"][1]]} for p in parts]
+    fuse(coords.cuda(), tsdf.cuda(), cin, 2, {}, save_mesh=False, panoptic_infos=infos)
+    C = fuse.global_volume[2]["C"].cpu().long()
+    o = torch.argsort((C[:, 0] * 100000 + C[:, 1]) * 100000 + C[:, 2])
+    assert np.array_equal(C[o].numpy(), g["f1_gC"])
+    assert np.array_equal(fuse.global_volume[2]["F"][:, :1].cpu()[o].numpy(), g["f1_gF"])
+    assert np.array_equal(fuse.global_instance.cpu()[o].numpy().reshape(-1, 1), g["f1_gI"])
+    assert np.array_equal(fuse.global_semantic.cpu()[o].numpy().reshape(-1, 1), g["f1_gS"])
+
+
 @pytest.mark.parametrize("n_keys,n_queries,n_heads", [(1, 80, 8), (63, 80, 8), (65, 96, 8), (5000, 80, 8), (105001, 80, 8), (777, 7, 2)])
 def test_fused_masked_attention_matches_fp64_softmax(cuda_lib, n_keys, n_queries, n_heads):
     """csrc/attention.cu vs a float64 masked softmax-attention (the nn.MultiheadAttention math of mask3dformer.py:70-130)."""

@@ -1,18 +1,25 @@
-"""End-to-end parity at BASELINE configs[1]'s FULL size (96^3, 9 x 640 x 480, the bench fragment: ~210 k level-2
-candidates, ~105 k final voxels): NeuConNet.forward on CUDA, teacher-forced on the CPU oracle's data-dependent decisions,
-against oracle/restate.py stage by stage -- the same assertions as tests/test_neucon_gpu.py makes on the 64^3 golden
-configuration.  The oracle needs 12-22 s of CPU for this fragment.
+"""End-to-end parity at BASELINE's FULL sizes: NeuConNet.forward on CUDA against oracle/restate.py (a CPU restatement
+pinned to the reference by the fixtures under tests/golden/; the torchsparse / spconv layer beneath it is itself a
+restatement).
 
-Marked xfail(strict=False): the test was written after the round's GPU budget was spent, so its first execution is the
-driver's round-end run; it must not turn the suite red on an untried size (an XPASS in the log is the expected
-outcome, and the marker goes away once it has been seen to pass)."""
+  * configs[1] (96^3, 9 x 640 x 480, the bench fragment: ~210 k level-2 candidates, ~105 k final voxels):
+      - a 3-fragment stream of ONE scene through the recurrent GRU state, teacher-forced on the oracle's data-dependent
+        decisions, stage by stage: voxel sets / union sites / aligned points bit-exact, floats within 1e-3 in the max
+        norm AND elementwise (|a-b| <= 1e-3 * max(|b|, 1e-2 * max|b|));
+      - the first fragment free-running (no teacher): at most 2e-4 of the final voxels may differ, every one of them
+        within 1e-4 of its occupancy threshold, TSDF on the common voxels within 1e-3.
+  * configs[4] (128^3, 18 x 960 x 720), one fragment, TSDF path, shipped caps (config/test.yaml:29): teacher-forced,
+    same assertions.
+
+The oracle needs 15-60 s of CPU per fragment at these sizes; the module-scoped fixtures run each once.
+"""
+import numpy as np
 import pytest
 import torch
 
 from eprecon_b200 import synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first execution at full size happens in the driver's round-end run")]
+pytestmark = [pytest.mark.gpu]
 RTOL = 1e-3
 
 
@@ -21,38 +28,140 @@ def rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
 
-def test_full_size_fragment_teacher_forced_matches_oracle(cuda_lib):
+def elementwise_ok(a, b, rtol=RTOL, floor=1e-2):
+    """|a-b| <= rtol * max(|b|, floor * max|b|) for every element (tighter than the max norm: small entries are bounded
+    relative to themselves down to 1 % of the tensor's scale)."""
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    bound = rtol * torch.maximum(b.abs(), floor * b.abs().max())
+    return bool(((a - b).abs() <= bound).all()), float(((a - b).abs() / bound).max())
+
+
+def close(a, b, what):
+    assert rel(a, b) < RTOL, (what, rel(a, b))
+    ok, worst = elementwise_ok(a, b)
+    assert ok, (what, "elementwise bound exceeded by x%.2f" % worst)
+
+
+def to_cuda(inputs):
+    return {k: (v.cuda() if torch.is_tensor(v) else ([t.cuda() for t in v] if isinstance(v, list) and torch.is_tensor(v[0]) else v))
+            for k, v in inputs.items()}
+
+
+def check_stages(tt, ot, out, oout, tag):
+    assert torch.equal(tt["init"]["coords"].cpu(), ot["init"]["coords"]), tag
+    assert torch.equal(tt["init"]["count"].cpu(), ot["init"]["count"]), tag
+    close(tt["init"]["occ"], ot["init"]["occ"], (tag, "init occ"))
+    for level in range(3):
+        a, b = tt[f"l{level}_pre_gru"], ot[f"l{level}_pre_gru"]
+        assert torch.equal(a["coords"].cpu(), b["coords"].int()), (tag, level)      # back-projected voxel set, bit-exact
+        assert torch.equal(a["pts"].cpu(), b["pts"]), (tag, level)                  # aligned-camera points, bit-exact
+        close(a["feat_in"], b["feat_in"], (tag, level, "feat_in"))
+        close(a["spvcnn"], b["spvcnn"], (tag, level, "spvcnn"))
+        a, b = tt[f"l{level}"], ot[f"l{level}"]
+        assert torch.equal(a["coords"].cpu().long(), b["coords"]), (tag, level)     # GRU-fusion union sites, bit-exact
+        close(a["feat_all"], b["feat_all"], (tag, level, "feat_all"))
+        close(a["tsdf"], b["tsdf"], (tag, level, "tsdf"))
+        close(a["occ"], b["occ"], (tag, level, "occ"))
+    assert torch.equal(out["coords"].cpu(), oout["coords"]), tag                    # final voxel indices, bit-exact
+    close(out["tsdf"], oout["tsdf"], (tag, "final tsdf"))                           # TSDF within 1e-3 relative
+
+
+@pytest.fixture(scope="module")
+def stream96(cuda_lib):
+    """Oracle + CUDA over fragments 0..2 of one scene at the bench size (recurrent state carried on both sides)."""
     from oracle import restate
     from eprecon_b200.neucon_network import NeuConNet
     cfg = synth.make_cfg()
     cfg.THRESHOLDS = list(synth.BENCH_THRESHOLDS)
     net = NeuConNet(cfg)
     sd = synth.synthetic_state_dict(net, 1)
-    inputs, fa, fb = synth.make_fragment(seed=1)
+    net = net.cuda().train()
+    state = restate.FusionState()
+    runs = []
+    for frag in range(3):
+        inputs, fa, fb = synth.make_fragment(seed=1, frag_index=frag)
+        ot = {}
+        with torch.no_grad():
+            oout = restate.neucon_forward(sd, cfg, fa, fb, inputs, state, trace=ot)
+        if oout is None or "coords" not in oout:
+            break
+        cin = to_cuda(inputs)
+        cin["scene"] = ["scene_fullsize_stream"]
+        net.trace, net.teacher = {}, ot
+        out, _ = net([[t.cuda() for t in f] for f in fa], [[t.cuda() for t in f] for f in fb], cin, {})
+        runs.append((frag, net.trace, ot, out, oout))
+        net.trace = None
+    return cfg, net, runs
+
+
+def test_full_size_fragment_teacher_forced_matches_oracle(stream96):
+    cfg, net, runs = stream96
+    assert len(runs) >= 1
+    frag, tt, ot, out, oout = runs[0]
+    assert oout["coords"].shape[0] > 90000
+    check_stages(tt, ot, out, oout, "frag0")
+
+
+def test_full_size_stream_through_recurrent_state(stream96):
+    """Fragments 1 and 2 of the same scene fuse with the state the earlier fragments left behind (GRUFusion feature mode)."""
+    cfg, net, runs = stream96
+    assert len(runs) == 3, "the oracle early-returned on a later fragment of the synthetic stream"
+    for frag, tt, ot, out, oout in runs[1:]:
+        # the union must really contain voxels that only the global state holds
+        assert tt["l2"]["coords"].shape[0] > tt["l2_pre_gru"]["coords"].shape[0], frag
+        check_stages(tt, ot, out, oout, f"frag{frag}")
+
+
+def test_full_size_free_running(stream96):
+    from eprecon_b200.neucon_network import NeuConNet
+    cfg, net, runs = stream96
+    frag, tt, ot, out_t, oout = runs[0]
+    inputs, fa, fb = synth.make_fragment(seed=1, frag_index=0)
+    cin = to_cuda(inputs)
+    cin["scene"] = ["scene_fullsize_free"]            # fresh scene state
+    net.trace, net.teacher = {}, None
+    out_f, _ = net([[t.cuda() for t in f] for f in fa], [[t.cuda() for t in f] for f in fb], cin, {})
+    ft = net.trace
+    net.trace = None
+    assert "coords" in out_f
+    key = lambda c: (c[:, 1].astype(np.int64) * 4096 + c[:, 2]) * 4096 + c[:, 3]  # noqa: E731
+    km, kr = key(out_f["coords"].cpu().numpy()), key(oout["coords"].numpy())
+    common, im, ir = np.intersect1d(km, kr, return_indices=True)
+    n_diff = len(km) + len(kr) - 2 * len(common)
+    assert n_diff <= max(8, int(2e-4 * len(kr))), n_diff
+    scale = oout["tsdf"].abs().max().item()
+    assert np.abs(out_f["tsdf"].cpu().numpy()[im] - oout["tsdf"].numpy()[ir]).max() <= RTOL * scale
+    # every decision that differs from the oracle's sits on a threshold: compare the occupancy flags level by level on the
+    # voxels both runs hold and require the oracle's logit of a flipped voxel to be within 1e-4 of the threshold
+    for level in range(3):
+        a, b = ft[f"l{level}"], ot[f"l{level}"]
+        ka, kb = key(a["coords"].cpu().numpy()), key(b["coords"].numpy())
+        _, ia, ib = np.intersect1d(ka, kb, return_indices=True)
+        fa_, fb_ = a["occupancy"].cpu().numpy()[ia], b["occupancy"].numpy()[ib]
+        flipped = fa_ != fb_
+        if flipped.any():
+            margins = np.abs(b["occ"].numpy().reshape(-1)[ib][flipped] - float(cfg.THRESHOLDS[level]))
+            assert margins.max() < 1e-4, (level, int(flipped.sum()), float(margins.max()))
+
+
+def test_highres_fragment_teacher_forced(cuda_lib):
+    """BASELINE configs[4]: 18 views, 960 x 720, 128^3, TSDF path, shipped caps."""
+    from oracle import restate
+    from eprecon_b200.neucon_network import NeuConNet
+    n_vox = (128, 128, 128)
+    cfg = synth.make_cfg(n_vox=n_vox)
+    cfg.THRESHOLDS = list(synth.HIGHRES_THRESHOLDS)
+    net = NeuConNet(cfg)
+    sd = synth.synthetic_state_dict(net, 1)
+    inputs, fa, fb = synth.make_fragment(seed=1, n_views=18, image_hw=(720, 960), n_vox=n_vox)
     ot = {}
     with torch.no_grad():
         oout = restate.neucon_forward(sd, cfg, fa, fb, inputs, restate.FusionState(), trace=ot)
+    assert oout is not None and "coords" in oout, "thresholds must keep the synthetic occupancy inside the shipped caps"
     assert oout["coords"].shape[0] > 90000
     net = net.cuda().train()
-    cin = {k: (v.cuda() if torch.is_tensor(v) else ([t.cuda() for t in v] if isinstance(v, list) and torch.is_tensor(v[0]) else v))
-           for k, v in inputs.items()}
-    cin["scene"] = ["scene_fullsize_parity"]
+    cin = to_cuda(inputs)
+    cin["scene"] = ["scene_highres_parity"]
     net.trace, net.teacher = {}, ot
     out, _ = net([[t.cuda() for t in f] for f in fa], [[t.cuda() for t in f] for f in fb], cin, {})
-    tt = net.trace
-    assert torch.equal(tt["init"]["coords"].cpu(), ot["init"]["coords"])
-    assert torch.equal(tt["init"]["count"].cpu(), ot["init"]["count"])
-    assert rel(tt["init"]["occ"], ot["init"]["occ"]) < RTOL
-    for level in range(3):
-        a, b = tt[f"l{level}_pre_gru"], ot[f"l{level}_pre_gru"]
-        assert torch.equal(a["coords"].cpu(), b["coords"].int()), level            # back-projected voxel set, bit-exact
-        assert torch.equal(a["pts"].cpu(), b["pts"]), level                        # aligned-camera points, bit-exact
-        assert rel(a["feat_in"], b["feat_in"]) < RTOL, level
-        assert rel(a["spvcnn"], b["spvcnn"]) < RTOL, level
-        a, b = tt[f"l{level}"], ot[f"l{level}"]
-        assert torch.equal(a["coords"].cpu().long(), b["coords"]), level           # GRU-fusion union sites, bit-exact
-        assert rel(a["feat_all"], b["feat_all"]) < RTOL, level
-        assert rel(a["tsdf"], b["tsdf"]) < RTOL, level
-        assert rel(a["occ"], b["occ"]) < RTOL, level
-    assert torch.equal(out["coords"].cpu(), oout["coords"])                        # final voxel indices, bit-exact
-    assert rel(out["tsdf"], oout["tsdf"]) < RTOL                                   # TSDF within 1e-3 relative
+    check_stages(net.trace, ot, out, oout, "highres")
