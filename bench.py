@@ -300,7 +300,7 @@ def run_ours(args):
 
     import torch.distributed as dist
     from eprecon_b200 import _lib, ops, synth
-    from eprecon_b200.dist import gather_fragments, merge_substitute
+    from eprecon_b200.dist import gather_to_holder, merge_substitute, pack_rows
     from eprecon_b200.neucon_network import NeuConNet
     from eprecon_b200.streams import FragmentStreams
 
@@ -343,23 +343,21 @@ def run_ours(args):
         assert "coords" in out, "forward early-returned (degenerate fragment)"
         return out
 
+    box_lo = [[int(rel[0]) + (rank * S + s) * 24, int(rel[1]), int(rel[2])] for s in range(S)]   # scenes side by side along x
+    box_hi = [[lo[0] + cfg.N_VOX[0], lo[1] + cfg.N_VOX[1], lo[2] + cfg.N_VOX[2]] for lo in box_lo]
+    shifts = [torch.tensor(lo, dtype=torch.int32, device=dev) for lo in box_lo]
+    skip_exchange = bool(os.environ.get("EPRECON_BENCH_NO_EXCHANGE"))   # diagnostic: split exchange cost from host contention
+
     def exchange(outs):
-        """The one exchange of the path (configs[3]): NCCL gather + merge of the step's sparse TSDFs (main thread / stream)."""
-        gcs, tss, boxes = [], [], []
-        for s, o in enumerate(outs):
-            off = (rank * S + s) * 24            # scenes side by side along x
-            shift = rel_dev.clone()
-            shift[0] += off
-            gcs.append(o["coords"][:, 1:].to(torch.int32) + shift)
-            tss.append(o["tsdf"].view(-1))
-        frags = gather_fragments(torch.cat(gcs), torch.cat(tss))
-        for r in range(world):
-            lo = rel.clone()
-            lo[0] += r * S * 24
-            hi = rel + torch.tensor(cfg.N_VOX)
-            hi[0] += (r * S + S - 1) * 24
-            boxes.append((lo.tolist(), hi.tolist()))
-        return merge_substitute(frags, boxes)
+        """The one exchange of the path (configs[3]): every rank sends its step's sparse TSDFs (unpadded int32 [n,4] rows) to
+        the holder (rank 0) over NCCL send/recv; the holder merges all fragments with ONE kernel (main thread / stream)."""
+        if skip_exchange:
+            return None
+        rows = [pack_rows(o["coords"][:, 1:].to(torch.int32) + shifts[s], o["tsdf"]) for s, o in enumerate(outs)]
+        got = gather_to_holder(rows, list(zip(box_lo, box_hi)), dst=0)
+        if got is None:
+            return None
+        return merge_substitute(got["rows"], got["frag_start"], got["boxes"])
 
     def barrier():
         if world > 1:
@@ -578,7 +576,8 @@ def run_ours(args):
                                                      "shared weights); value = fragments completed / device time",
                        "sizes": fs.nets[0].last_sizes, "thresholds": cfg.THRESHOLDS,
                        "l2": f"inputs rotated over {n_copies} HBM-resident copies ({n_copies * 54} MB of feature maps > 126 MB L2)",
-                       "multi_gpu": f"{S} fragments per rank per step + NCCL all_gather/merge of the step's global sparse TSDF" if world > 1 else "n/a"},
+                       "multi_gpu": (f"{S} fragments per rank per step + NCCL send/recv of the step's sparse TSDF rows to the holder (rank 0) + one merge "
+                                     "kernel there" + (" [EXCHANGE DISABLED: diagnostic run]" if skip_exchange else "")) if world > 1 else "n/a"},
             "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": h2d_bytes * S, "d2h_bytes_per_step": d2h[0] * S,
                     "ms_per_step": ms_e2e / K},
             "single_stream": single,

@@ -51,7 +51,7 @@ inline int bit_length(long long v) {
   return b;
 }
 
-struct Conv { const float* w; const float* w_hi; const float* w_lo; const float* bias; int K, cin, cout, npad; };
+struct Conv { const float* w; const float* w_hi; const float* w_lo; const uint16_t* w_hl; const float* bias; int K, cin, cout, npad; };
 struct Norm { const float* gamma; const float* beta; float eps; int c; };
 
 struct Reader {
@@ -61,8 +61,9 @@ struct Reader {
   Conv conv() {
     Conv c;
     c.w = (const float*)(uintptr_t)p[0]; c.w_hi = (const float*)(uintptr_t)p[1]; c.w_lo = (const float*)(uintptr_t)p[2];
-    c.bias = (const float*)(uintptr_t)p[3]; c.K = (int)p[4]; c.cin = (int)p[5]; c.cout = (int)p[6]; c.npad = (int)p[7];
-    p += 8;
+    c.w_hl = (const uint16_t*)(uintptr_t)p[3];
+    c.bias = (const float*)(uintptr_t)p[4]; c.K = (int)p[5]; c.cin = (int)p[6]; c.cout = (int)p[7]; c.npad = (int)p[8];
+    p += 9;
     return c;
   }
   Norm norm() {
@@ -268,8 +269,10 @@ Mat devoxelize(Exec& e, const Mat& v, int c, const int32_t* idx, const float* w,
   return o;
 }
 
-// out[j,:cout] = bias + sum_k W[k]^T x[nbr[j,k]]; K == 1 runs on the fp32 FFMA kernel, K > 1 on tcgen05 3xTF32
-Mat spconv(Exec& e, const float* x, int ldx, const Conv& cv, const int32_t* nbr, int m_out, float** part,
+// out[j,:cout] = bias + sum_k W[k]^T x[nbr[j,k]]; K == 1 runs on the fp32 FFMA kernel, K > 1 on the tensor cores: the TMA
+// gather kernel on half-pair operands (csrc/spconv_hl.cu; the input's m_in rows are split right here) when the descriptor
+// carries w_hl, else the round-1 3xTF32 kernel
+Mat spconv(Exec& e, const float* x, int ldx, int m_in, const Conv& cv, const int32_t* nbr, int m_out, float** part,
            float* out = nullptr, int ld_out = 0) {
   const int c4 = ceil4(cv.cout);
   Mat o{out, ld_out};
@@ -282,6 +285,15 @@ Mat spconv(Exec& e, const float* x, int ldx, const Conv& cv, const int32_t* nbr,
   if (part) { pp = alloc<float>(e, (size_t)ep_spconv_num_row_tiles(m_out) * 2 * cv.cout); *part = pp; }
   if (cv.K == 1) {
     RUN(e, 1, ep_spconv_fwd(x, ldx, cv.cin, nbr, 1, cv.w, c4, cv.cout, cv.bias, o.p, o.ld, m_out, pp, e.st));
+  } else if (cv.w_hl) {
+    const size_t mark = e.off;
+    uint16_t* xs = alloc<uint16_t>(e, (size_t)m_in * ep_hl_slabs(cv.cin) * 64);
+    RUN(e, 1, ep_hl_split_rows(x, ldx, cv.cin, m_in, xs, nullptr, e.st));
+    const size_t wsb = ep_spconv_hl_workspace_bytes(m_out, cv.npad, cv.K);
+    void* ws = wsb ? (void*)alloc<char>(e, wsb) : nullptr;
+    RUN(e, wsb ? 2 : 1, ep_spconv_hl_fwd(xs, m_in, cv.cin, nbr, cv.K, cv.w_hl, cv.npad, cv.cout, cv.bias, o.p, o.ld, m_out, pp, ws,
+                                        wsb, 0, e.st));
+    if (!e.err) e.off = mark;
   } else {
     const size_t mark = e.off;
     const size_t wsb = ep_spconv_tc_workspace_bytes(m_out, cv.npad, cv.K);
@@ -299,10 +311,10 @@ float* bn_ss(Exec& e, const float* part, int m, const Norm& bn) {
   return ss;
 }
 
-Mat conv_bn_relu(Exec& e, const float* x, int ldx, const int32_t* nbr, const Conv& cv, const Norm& bn, int m_out,
+Mat conv_bn_relu(Exec& e, const float* x, int ldx, int m_in, const int32_t* nbr, const Conv& cv, const Norm& bn, int m_out,
                  float* out = nullptr, int ld_out = 0) {
   float* part = nullptr;
-  Mat y = spconv(e, x, ldx, cv, nbr, m_out, &part, out, ld_out);
+  Mat y = spconv(e, x, ldx, m_in, cv, nbr, m_out, &part, out, ld_out);
   const float* ss = bn_ss(e, part, m_out, bn);
   RUN(e, 1, ep_affine_act(y.p, y.ld, ss, nullptr, 0, nullptr, 1, m_out, cv.cout, y.p, y.ld, e.st));
   return y;
@@ -319,15 +331,15 @@ ResBlock read_res(Reader& r) {
 }
 
 Mat residual_block(Exec& e, const Mat& x, const int32_t* nbr, const ResBlock& b, int m) {
-  Mat t = conv_bn_relu(e, x.p, x.ld, nbr, b.c1, b.b1, m);
+  Mat t = conv_bn_relu(e, x.p, x.ld, m, nbr, b.c1, b.b1, m);
   float* part_u = nullptr;
-  Mat u = spconv(e, t.p, t.ld, b.c2, nbr, m, &part_u);
+  Mat u = spconv(e, t.p, t.ld, m, b.c2, nbr, m, &part_u);
   const float* ss_u = bn_ss(e, part_u, m, b.b2);
   if (!b.has_down) {
     RUN(e, 1, ep_affine_act(u.p, u.ld, ss_u, x.p, x.ld, nullptr, 1, m, b.c2.cout, u.p, u.ld, e.st));
   } else {
     float* part_d = nullptr;
-    Mat d = spconv(e, x.p, x.ld, b.cd, nullptr, m, &part_d);
+    Mat d = spconv(e, x.p, x.ld, m, b.cd, nullptr, m, &part_d);
     const float* ss_d = bn_ss(e, part_d, m, b.bd);
     RUN(e, 1, ep_affine_act(u.p, u.ld, ss_u, d.p, d.ld, ss_d, 1, m, b.c2.cout, u.p, u.ld, e.st));
   }
@@ -349,8 +361,8 @@ struct SConv { Conv conv; Conv lin; };
 Mat sconv3d(Exec& e, const SConv& s, const float* feat, int ldf, int n, PointCloud& pc, const Globals& G,
             const int32_t* tap_idx, const float* tap_w) {
   Mat x = voxelize(e, pc.csr1, feat, ldf, s.conv.cin);
-  Mat y = spconv(e, x.p, x.ld, s.conv, kmap_k3(e, pc.vox, G), pc.vox.m, nullptr);
-  Mat lin = spconv(e, feat, ldf, s.lin, nullptr, n, nullptr);
+  Mat y = spconv(e, x.p, x.ld, pc.vox.m, s.conv, kmap_k3(e, pc.vox, G), pc.vox.m, nullptr);
+  Mat lin = spconv(e, feat, ldf, n, s.lin, nullptr, n, nullptr);
   return devoxelize(e, y, s.conv.cout, tap_idx, tap_w, n, lin.p, lin.ld);
 }
 
@@ -515,7 +527,7 @@ int ep_exec_spvcnn(const int64_t* desc, const int64_t* globals, const float* pts
   build_pc(e, pc, pts, n, vres, true);                                             // initial_voxelize
   VoxelSet& v0 = pc.vox;
   Mat x0 = voxelize(e, pc.csr1, feat, ld_feat, cin0);
-  x0 = conv_bn_relu(e, x0.p, x0.ld, kmap_k3(e, v0, G), stem, stem_bn, v0.m);       // stem
+  x0 = conv_bn_relu(e, x0.p, x0.ld, v0.m, kmap_k3(e, v0, G), stem, stem_bn, v0.m);       // stem
   const int32_t* idx1; const float* w1;
   taps(e, pc, v0, idx1, w1);
   Mat z0 = devoxelize(e, x0, cs[0], idx1, w1, n, nullptr, 0);                      // voxel_to_point(x0, z)
@@ -523,31 +535,31 @@ int ep_exec_spvcnn(const int64_t* desc, const int64_t* globals, const float* pts
   VoxelSet v1, v2;
   int32_t *down01, *up10, *down12, *up21;
   downsample(e, v0, G, v1, down01, up10);
-  x1 = conv_bn_relu(e, x1.p, x1.ld, down01, down1, down1_bn, v1.m);
+  x1 = conv_bn_relu(e, x1.p, x1.ld, v0.m, down01, down1, down1_bn, v1.m);
   x1 = residual_block(e, x1, kmap_k3(e, v1, G), s1a, v1.m);
   x1 = residual_block(e, x1, kmap_k3(e, v1, G), s1b, v1.m);
   downsample(e, v1, G, v2, down12, up21);
-  Mat x2 = conv_bn_relu(e, x1.p, x1.ld, down12, down2, down2_bn, v2.m);
+  Mat x2 = conv_bn_relu(e, x1.p, x1.ld, v1.m, down12, down2, down2_bn, v2.m);
   x2 = residual_block(e, x2, kmap_k3(e, v2, G), s2a, v2.m);
   x2 = residual_block(e, x2, kmap_k3(e, v2, G), s2b, v2.m);
   const int32_t* idx4; const float* w4;
   taps(e, pc, v2, idx4, w4);
-  Mat p0 = conv_bn_relu(e, z0.p, z0.ld, nullptr, pt0, pt0_bn, n);                  // point_transforms[0](z0.F)
+  Mat p0 = conv_bn_relu(e, z0.p, z0.ld, n, nullptr, pt0, pt0_bn, n);                  // point_transforms[0](z0.F)
   Mat z1 = devoxelize(e, x2, cs[2], idx4, w4, n, p0.p, p0.ld);
   const Csr csr2 = csr_for(e, pc, v2);
   Mat y3 = voxelize(e, csr2, z1.p, z1.ld, cs[2]);                                  // point_to_voxel(x2, z1)
   // up1: transposed conv to stride 2, concat skip x1, two residual blocks
   Mat cat1{alloc<float>(e, (size_t)v1.m * (cs[3] + cs[1])), cs[3] + cs[1]};
-  conv_bn_relu(e, y3.p, y3.ld, up21, dec1, dec1_bn, v1.m, cat1.p, cat1.ld);
+  conv_bn_relu(e, y3.p, y3.ld, v2.m, up21, dec1, dec1_bn, v1.m, cat1.p, cat1.ld);
   copy_cols(e, x1.p, x1.ld, v1.m, cs[1], cat1.p + cs[3], cat1.ld);
   y3 = residual_block(e, cat1, kmap_k3(e, v1, G), u1a, v1.m);
   y3 = residual_block(e, y3, kmap_k3(e, v1, G), u1b, v1.m);
   Mat cat0{alloc<float>(e, (size_t)v0.m * (cs[4] + cs[0])), cs[4] + cs[0]};
-  conv_bn_relu(e, y3.p, y3.ld, up10, dec2, dec2_bn, v0.m, cat0.p, cat0.ld);
+  conv_bn_relu(e, y3.p, y3.ld, v1.m, up10, dec2, dec2_bn, v0.m, cat0.p, cat0.ld);
   copy_cols(e, x0.p, x0.ld, v0.m, cs[0], cat0.p + cs[4], cat0.ld);
   Mat y4 = residual_block(e, cat0, kmap_k3(e, v0, G), u2a, v0.m);
   y4 = residual_block(e, y4, kmap_k3(e, v0, G), u2b, v0.m);
-  Mat p1 = conv_bn_relu(e, z1.p, z1.ld, nullptr, pt1, pt1_bn, n);                  // point_transforms[1](z1.F)
+  Mat p1 = conv_bn_relu(e, z1.p, z1.ld, n, nullptr, pt1, pt1_bn, n);                  // point_transforms[1](z1.F)
   devoxelize(e, y4, cs[4], idx1, w1, n, p1.p, p1.ld, out, ld_out);
   return finish(e, stats);
 }
@@ -605,13 +617,13 @@ int ep_exec_linear4x(const int64_t* desc, const float* x, int ld_x, int64_t m64,
     if (ld_x < ceil4(H.c_in)) return EP_ERR_ARG;
     float* out = (float*)(uintptr_t)outs[hd];
     const size_t mark = e.off;
-    Mat y1 = spconv(e, x, ld_x, l1, nullptr, m, nullptr);
+    Mat y1 = spconv(e, x, ld_x, m, l1, nullptr, m, nullptr);
     layernorm(e, y1.p, y1.ld, nullptr, 0, 0, n1, 1, m, y1.p, y1.ld);
-    Mat y2 = spconv(e, y1.p, y1.ld, l2, nullptr, m, nullptr);
+    Mat y2 = spconv(e, y1.p, y1.ld, m, l2, nullptr, m, nullptr);
     layernorm(e, y2.p, y2.ld, nullptr, 0, 0, n2, 1, m, y2.p, y2.ld);
     const int c4 = ceil4(c_out);
     if (c4 != c_out) zero_bytes(e, out, sizeof(float) * (size_t)m * c4);
-    spconv(e, y2.p, y2.ld, l3, nullptr, m, nullptr, out, c4);
+    spconv(e, y2.p, y2.ld, m, l3, nullptr, m, nullptr, out, c4);
     if (use_res) RUN(e, 1, ep_affine_act(out, c4, nullptr, y2.p, y2.ld, nullptr, 0, m, c_out, out, c4, e.st));
     if (!e.err) e.off = mark;
   }
@@ -654,7 +666,7 @@ int ep_exec_init_head(const int64_t* desc, const int64_t* globals, const float* 
   // ELAN: cat = [f1 | f2 | c3 | c4 | c5 | c6]
   Mat cat{alloc<float>(e, (size_t)m * 4 * d), 4 * d};
   auto block = [&](int i, const float* in, int ld_in, float* out, int ld_o) {
-    Mat y = spconv(e, in, ld_in, ec[i], nbr_of(ec[i]), m, nullptr);
+    Mat y = spconv(e, in, ld_in, m, ec[i], nbr_of(ec[i]), m, nullptr);
     if (!out) { out = y.p; ld_o = y.ld; }
     layernorm(e, y.p, y.ld, nullptr, 0, 0, en[i], 1, m, out, ld_o);
     return Mat{out, ld_o};
@@ -667,13 +679,13 @@ int ep_exec_init_head(const int64_t* desc, const int64_t* globals, const float* 
   block(5, cat.p + 2 * d + 2 * hc, cat.ld, cat.p + 2 * d + 3 * hc, cat.ld);
   x = block(6, cat.p, cat.ld, nullptr, 0);
   for (int i = 0; i < 3; ++i) {
-    Mat y = spconv(e, x.p, x.ld, sc[i], nbr_of(sc[i]), m, nullptr);
+    Mat y = spconv(e, x.p, x.ld, m, sc[i], nbr_of(sc[i]), m, nullptr);
     layernorm(e, y.p, y.ld, x.p, x.ld, 1, sn[i], 0, m, y.p, y.ld);
     x = y;
   }
   zero_bytes(e, occ, sizeof(float) * (size_t)m * 4);
   float* part4 = nullptr;
-  spconv(e, x.p, x.ld, subm4, nbr_of(subm4), m, &part4, occ, 4);
+  spconv(e, x.p, x.ld, m, subm4, nbr_of(subm4), m, &part4, occ, 4);
   const float* ss4 = bn_ss(e, part4, m, norm4);
   RUN(e, 1, ep_affine_act(occ, 4, ss4, nullptr, 0, nullptr, 0, m, 1, occ, 4, e.st));
   return finish(e, stats);

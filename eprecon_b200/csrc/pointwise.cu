@@ -245,3 +245,79 @@ int ep_threshold_flags(const float* x, int ld, int64_t n, float thr, int mode, u
 }
 
 }  // extern "C"
+
+// ---- train-mode BatchNorm2d (+ residual-before, + ReLU) for the dense 2-D fusion (models/modules.py:313-399,
+// models/occupancy_initialization.py:41-58): statistics over (N, H, W) of an NCHW map.  Two launches per layer instead of
+// ATen's var_mean + rsqrt + mul + sub + addcmul + relu chain (8 launches inside the captured graph).
+namespace {
+constexpr int BN2D_CHUNKS = 16;   // partial sums per channel: fixed count, fixed order -> deterministic
+
+// x (+ relu_pre?  y = relu(x) + res : x).  part[c][chunk] = (sum, sumsq) in double over the chunk's elements
+__global__ void __launch_bounds__(256)
+bn2d_stats_kernel(const float* __restrict__ x, const float* __restrict__ res, int relu_pre, int n_img, int c, int hw,
+                  double2* __restrict__ part) {
+  const int ch = blockIdx.x, chunk = blockIdx.y;
+  const long long total = (long long)n_img * hw;
+  const long long per = (total + BN2D_CHUNKS - 1) / BN2D_CHUNKS;
+  const long long beg = chunk * per, end = min(total, beg + per);
+  double s = 0.0, q = 0.0;
+  for (long long e = beg + threadIdx.x; e < end; e += blockDim.x) {
+    const long long img = e / hw, p = e - img * hw;
+    const size_t off = ((size_t)img * c + ch) * hw + p;
+    float v = x[off];
+    if (relu_pre) v = fmaxf(v, 0.f);
+    if (res) v += res[off];
+    s += v;
+    q += (double)v * v;
+  }
+  __shared__ double ss[256], sq[256];
+  ss[threadIdx.x] = s; sq[threadIdx.x] = q;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) { ss[threadIdx.x] += ss[threadIdx.x + d]; sq[threadIdx.x] += sq[threadIdx.x + d]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[ch * BN2D_CHUNKS + chunk] = make_double2(ss[0], sq[0]);
+}
+
+__global__ void __launch_bounds__(256)
+bn2d_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, int relu_pre, int n_img, int c, int hw,
+                  const double2* __restrict__ part, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                  int relu_post, float* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n_img * c * hw;
+  if (t >= total) return;
+  const int ch = (int)((t / hw) % c);
+  double s = 0.0, q = 0.0;
+#pragma unroll
+  for (int k = 0; k < BN2D_CHUNKS; ++k) { const double2 p = part[ch * BN2D_CHUNKS + k]; s += p.x; q += p.y; }
+  const double cnt = (double)n_img * hw;
+  const double mean = s / cnt;
+  const double var = fmax(q / cnt - mean * mean, 0.0);
+  const float scale = gamma[ch] * rsqrtf((float)var + eps);
+  const float shift = beta[ch] - (float)mean * scale;
+  float v = x[t];
+  if (relu_pre) v = fmaxf(v, 0.f);
+  if (res) v += res[t];
+  v = fmaf(v, scale, shift);
+  if (relu_post) v = fmaxf(v, 0.f);
+  out[t] = v;
+}
+}  // namespace
+
+extern "C" {
+size_t ep_bn2d_workspace_bytes(int c) { return (size_t)c * BN2D_CHUNKS * sizeof(double2); }
+
+// out = [relu]( BN_batchstats( res ? relu?(x) + res : relu?(x) ) ); x, res, out: NCHW f32 [n_img, c, hw] contiguous.
+int ep_bn2d_train(const float* x, const float* res, int relu_pre, int n_img, int c, int hw, const float* gamma, const float* beta,
+                  float eps, int relu_post, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (n_img < 1 || c < 1 || hw < 1 || !gamma || !beta) return EP_ERR_ARG;
+  if (workspace_bytes < ep_bn2d_workspace_bytes(c) || ((uintptr_t)workspace & 15)) return EP_ERR_WORKSPACE;
+  double2* part = reinterpret_cast<double2*>(workspace);
+  bn2d_stats_kernel<<<dim3(c, BN2D_CHUNKS), 256, 0, stream>>>(x, res, relu_pre, n_img, c, hw, part);
+  const long long total = (long long)n_img * c * hw;
+  bn2d_apply_kernel<<<ep_div_up(total, 256), 256, 0, stream>>>(x, res, relu_pre, n_img, c, hw, part, gamma, beta, eps, relu_post, out);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+}  // extern "C"

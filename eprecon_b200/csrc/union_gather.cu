@@ -139,3 +139,48 @@ int ep_lookup_marks(const int32_t* coords, int64_t n, int step, int dx, int dy, 
   return EP_OK;
 }
 }  // extern "C"
+
+// ---- global-volume merge on the holder rank (BASELINE configs[3]; rule from GRUFusion(direct_substitute=True),
+// models/gru_fusion.py:93-94,198-204: a fragment REPLACES every global voxel inside its bounding volume).  Fragments are
+// applied in order, so a row of fragment f survives iff no LATER fragment's box contains it: one pass over all rows at
+// once instead of the reference's per-fragment mask + cat (O(F * rows) tensor traffic, F dependent steps).
+namespace {
+constexpr int kMaxMergeFragments = 1024;
+__global__ void __launch_bounds__(256)
+merge_substitute_flags_kernel(const int4* __restrict__ rows, int n, const int* __restrict__ frag_start,
+                              const int* __restrict__ boxes, int F, uint8_t* __restrict__ flags) {
+  __shared__ int s_start[kMaxMergeFragments + 1];
+  __shared__ int s_box[kMaxMergeFragments * 6];
+  for (int i = threadIdx.x; i <= F; i += blockDim.x) s_start[i] = frag_start[i];
+  for (int i = threadIdx.x; i < 6 * F; i += blockDim.x) s_box[i] = boxes[i];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = F;            // fragment of row i: last f with s_start[f] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (s_start[mid] <= i) lo = mid; else hi = mid;
+  }
+  const int4 r = rows[i];
+  bool keep = true;
+  for (int f = lo + 1; f < F && keep; ++f) {
+    if (s_start[f + 1] == s_start[f]) continue;      // an empty fragment substitutes nothing (the reference skips it)
+    const int* b = s_box + 6 * f;
+    keep = !(r.x >= b[0] && r.x < b[3] && r.y >= b[1] && r.y < b[4] && r.z >= b[2] && r.z < b[5]);
+  }
+  flags[i] = keep;
+}
+}  // namespace
+
+extern "C" {
+// rows int32 [n,4] = (x, y, z, tsdf bits) of F fragments back to back; frag_start int32 [F+1]; boxes int32 [F,6]
+// (lo xyz inclusive, hi xyz exclusive, global voxel units).  flags[i] = 1 iff row i survives the in-order substitution.
+int ep_merge_substitute_flags(const int32_t* rows, int64_t n, const int32_t* frag_start, const int32_t* boxes, int n_fragments,
+                              uint8_t* flags, cudaStream_t stream) {
+  if (n <= 0 || n_fragments < 1 || n_fragments > kMaxMergeFragments) return EP_ERR_ARG;
+  merge_substitute_flags_kernel<<<ep_div_up(n, 256), 256, 0, stream>>>((const int4*)rows, (int)n, frag_start, boxes, n_fragments,
+                                                                      flags);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+}  // extern "C"

@@ -6,7 +6,8 @@ initialisation head) ctypes calls the Python mirrors in modules.py make, launchi
 different CUDA streams (eprecon_b200.streams.FragmentStreams) really run their host side in parallel.
 
 Descriptor layout (flat int64, read sequentially by csrc/executor.cu::Reader):
-  conv  = [W_ffma, W_umma_hi, W_umma_lo, bias, K, cin, cout, npad]      (pointers are 0 when unused)
+  conv  = [W_ffma, W_umma_hi, W_umma_lo, W_hl, bias, K, cin, cout, npad] (pointers are 0 when unused; W_hl != 0 selects
+          the TMA-gather kernel on half-pair operands, csrc/spconv_hl.cu)
   norm  = [gamma, beta, float32 bits of eps, channels]                  (BatchNorm1d or LayerNorm)
   res   = conv1, bn1, conv2, bn2, has_down, [conv_down, bn_down]
   SPVCNN      = cs[0..4], cin, stem conv+bn, down1 conv+bn, res, res, down2 conv+bn, res, res, pt0 lin+bn,
@@ -34,7 +35,7 @@ _END = {"spvcnn": 0x5350564E, "gru": 0x47525546, "lin4x": 0x4C345854, "init": 0x
 
 
 def enabled():
-    return ENABLED and ops.SPCONV_IMPL == "tf32x3"
+    return ENABLED and ops.SPCONV_IMPL in ("tf32x3", "hl")
 
 
 # ----------------------------------------------------------------------------------------------- descriptors
@@ -52,13 +53,17 @@ class _Builder:
     def _conv(self, W, cout, bias):
         """W: FFMA-layout weights [K, cin, ceil4(cout)] (prepared by the module)."""
         K, cin = int(W.shape[0]), int(W.shape[1])
-        hi = lo = None
+        hi = lo = hl = None
         npad = 0
         if K > 1:
-            hi, lo, npad = ops._umma_weights(W, cout, 3)
-        self.keep += [W, hi, lo, bias]
+            if ops.SPCONV_IMPL == "hl":
+                hl, npad = ops._hl_weights(W, cout)
+            else:
+                hi, lo, npad = ops._umma_weights(W, cout, 3)
+        self.keep += [W, hi, lo, hl, bias]
         self.v += [W.data_ptr(), hi.data_ptr() if hi is not None else 0, lo.data_ptr() if lo is not None else 0,
-                   bias.data_ptr() if bias is not None else 0, K, cin, int(cout), int(npad)]
+                   hl.data_ptr() if hl is not None else 0, bias.data_ptr() if bias is not None else 0, K, cin, int(cout),
+                   int(npad)]
 
     def spconv(self, p):      # modules.SpConv3dParams (torchsparse conv: no bias)
         self._conv(p.prepared(), p.outc, None)
@@ -150,6 +155,7 @@ def _desc(owner, key, obj, build):
     moved (.to / .cuda) or modified in place (load_state_dict, optimizer step).  The Parameter objects themselves are
     looked up once: walking nn.Module trees on every call cost 3 ms per fragment."""
     cache = owner.__dict__.setdefault("_exec_desc", {})
+    key = (key, ops.SPCONV_IMPL)
     hit = cache.get(key)
     if hit is not None:
         tag = tuple((p.data_ptr(), p._version) for p in hit[0])

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import executor, ops, sparse
+from . import _lib, executor, ops, sparse
 from .ops import ceil4
 from .tensor import PointTensor  # noqa: F401  (re-exported for callers that build inputs)
 
@@ -487,15 +487,25 @@ class Panoptic_Feat_Fusion(nn.Module):
 
 
 # --------------------------------------------------------------------- dense 2-D blocks (stay on cuDNN)
-def _bn2d(x, bn):
-    """Train-mode BatchNorm2d (statistics of the current views, biased variance) as one var_mean reduction + one fused
-    elementwise pass: cuDNN's small-batch training kernel takes ~55 us per call on these 9 x C x 60 x 80 maps, this takes
-    ~15 us, and all of it sits inside the captured CUDA graph.  Falls back to nn.BatchNorm2d.forward in eval mode."""
+def _bn2d(x, bn, res=None, relu_pre=False, relu_post=False):
+    """Train-mode BatchNorm2d (statistics of the current views, biased variance) of `relu_pre ? relu(x) : x` (+ res),
+    optionally followed by ReLU: ONE statistics kernel + ONE apply kernel (csrc/pointwise.cu::ep_bn2d_train) instead of
+    ATen's var_mean / rsqrt / mul / sub / addcmul / relu chain (8 launches per layer; cuDNN's small-batch training kernel
+    takes ~55 us per call on these 9 x C x 60 x 80 maps).  All of it sits inside the captured CUDA graph."""
     if not bn.training:
-        return bn(x)
-    var, mean = torch.var_mean(x, dim=(0, 2, 3), unbiased=False, keepdim=True)
-    scale = bn.weight.view(1, -1, 1, 1) * torch.rsqrt(var + bn.eps)
-    return torch.addcmul(bn.bias.view(1, -1, 1, 1) - mean * scale, x, scale)
+        raise RuntimeError("eprecon_b200 runs BatchNorm with batch statistics only (reference main.py:357 evaluates in train())")
+    if not x.is_cuda:
+        raise _lib.EpreconError("eprecon_b200 has no CPU path")
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty_like(x)
+    L = _lib.lib()
+    wsb = L.ep_bn2d_workspace_bytes(c)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    _lib.check(L.ep_bn2d_train(x.data_ptr(), res.contiguous().data_ptr() if res is not None else 0, int(relu_pre), n, c, h * w,
+                               bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), int(relu_post), out.data_ptr(),
+                               ws.data_ptr(), wsb, ops.stream_ptr()), "ep_bn2d_train")
+    return out
 
 
 class Conv2d_Block(nn.Module):
@@ -506,7 +516,7 @@ class Conv2d_Block(nn.Module):
         self.act = nn.ReLU()
 
     def forward(self, x):
-        return self.act(_bn2d(self.conv(x), self.bn))
+        return _bn2d(self.conv(x), self.bn, relu_post=True)
 
 
 class Conv2d_Residual_Block(nn.Module):
@@ -517,7 +527,7 @@ class Conv2d_Residual_Block(nn.Module):
         self.relu = nn.ReLU()
 
     def forward(self, x):
-        return _bn2d(self.relu(self.conv(x)) + x, self.bn)
+        return _bn2d(self.conv(x), self.bn, res=x, relu_pre=True)
 
 
 class ELAN(nn.Module):
@@ -552,6 +562,6 @@ class Fusion_Block(nn.Module):
         self.ELAN = ELAN(C)
 
     def forward(self, x):
-        out = self.relu(_bn2d(self.conv1(x), self.bn1))
-        out = self.relu(_bn2d(self.conv2(out), self.bn2))
+        out = _bn2d(self.conv1(x), self.bn1, relu_post=True)
+        out = _bn2d(self.conv2(out), self.bn2, relu_post=True)
         return self.ELAN(out)

@@ -140,6 +140,11 @@ int ep_affine_act(const float* a, int ld_a, const float* ss_a, const float* b, i
 int ep_layernorm(const float* x, int ld_x, const float* res, int ld_res, int relu_before, const float* gamma,
                  const float* beta, float eps, int relu_after, int64_t m, int c, float* out, int ld_out,
                  cudaStream_t stream);
+/* train-mode BatchNorm2d of the dense 2-D fusion (models/modules.py:313-399; occupancy_initialization.py:41-58): batch
+ * statistics over (N,H,W), optional ReLU + residual before (Conv2d_Residual_Block), optional ReLU after; 2 launches. */
+size_t ep_bn2d_workspace_bytes(int c);
+int ep_bn2d_train(const float* x, const float* res, int relu_pre, int n_img, int c, int hw, const float* gamma, const float* beta,
+                  float eps, int relu_post, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int ep_gru_rh(const float* r_pre, int ld_r, const float* h, int ld_h, const float* x, int ld_x, int64_t m, int c,
               float* out, int ld_out, cudaStream_t stream);
 int ep_gru_out(const float* z_pre, int ld_z, const float* q_pre, int ld_q, const float* h, int ld_h, int64_t m, int c,
@@ -167,6 +172,10 @@ int ep_union_flags(const int32_t* vol_a, const int32_t* vol_b, int64_t n, uint8_
 int ep_union_sites(const int32_t* sites, int64_t u, int dy, int dz, int batch, int scale, const int32_t* vol_a,
                    const int32_t* vol_b, int32_t* out_coords, int32_t* row_a, int32_t* row_b, cudaStream_t stream);
 
+/* global-volume merge on the holder rank (configs[3]): in-order substitute-inside-bounding-volume rule of
+ * GRUFusion(direct_substitute=True) (models/gru_fusion.py:93-94,198-204) over all gathered rows at once. */
+int ep_merge_substitute_flags(const int32_t* rows, int64_t n, const int32_t* frag_start, const int32_t* boxes, int n_fragments,
+                              uint8_t* flags, cudaStream_t stream);
 
 /* ---- panoptic level alignment (models/neucon_network.py:516-544): hash-free parent marking instead of an O(N*M) compare */
 int ep_mark_parents(const int32_t* coords, int64_t n, int step, int dx, int dy, int dz, int bs, uint8_t* vol,
