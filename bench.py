@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — fragments/sec of the EPRecon feature-volume hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload fragment|stream16|highres]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One step = one NeuConNet.forward over one synthetic 9x640x480 fragment through the full 3-level (24/48/96^3)
@@ -37,13 +37,26 @@ SAMPLE_TEXT = {2: "one FULL 9x640x480 fragment per step: occupancy initialisatio
                   "counted as 0.151 of a fragment (its share of the oracle's time on the build container)",
                0: "per step: one full-size fragment through occupancy initialisation + level 0 only (configs[0]); counted as 0.058 "
                   "of a fragment (its share of the oracle's time on the build container)"}
+PORT_NOTE = ("; the arm is oracle/restate.py, a CPU restatement of the reference's algorithm pinned to the unmodified reference by the fixtures "
+             "under tests/golden/ -- the reference modules themselves need torchsparse / spconv (not installable offline) and "
+             "/root/reference does not exist on the GPU box")
 METRIC = "fragments/sec (9x640x480, 3-level 96^3)"
 DEFAULT_STREAMS = 8   # fragments in flight per GPU (EPRECON_STREAMS overrides); 1/4/8 streams measured 44/70/81 fragments/s
-# dram__bytes_read.sum + dram__bytes_write.sum of the largest spconv_tc_kernel<3> launch of a fragment (ncu --set full)
-SPCONV_TRAFFIC = {"bytes": 84.4e6, "note": "dram read 80.0 MB + write 4.4 MB of the level-2 stem launch (74->8 ch, 193 k rows, K=27; "
-                                           "algorithmic bytes of that launch: 57 MB rows in + 6 MB rows out + 21 MB neighbour table "
-                                           "= 84 MB, i.e. no DRAM re-reads) from profiles/r01_spconv_tc_v7_level2_ncu_summary.txt"}
 WORKLOAD = "configs[1]: single 9-view 640x480 fragment, 3-level 24/48/96^3 @4cm, GRU fusion (fresh scene), TSDF+occ heads"
+# --workload variants make BASELINE configs[2] / configs[4] driver-runnable (the default stays configs[1], the one `metric` is quoted on)
+WORKLOADS = {
+    "fragment": {"text": WORKLOAD, "metric": METRIC, "n_views": 9, "image_hw": (480, 640), "n_vox": (96, 96, 96), "thresholds": "BENCH_THRESHOLDS",
+                 "stream_len": 1, "panoptic": False},
+    "stream16": {"text": "configs[2]: stream of 16 overlapping 9-view 640x480 fragments of ONE scene per stream slot, GRU feature fusion across "
+                         "fragments, full mask3dformer panoptic head, scene-level TSDF/instance/semantic fusion; shipped caps",
+                 "metric": "fragments/sec (9x640x480, 3-level 96^3, 16-fragment scene stream + panoptic head)", "n_views": 9,
+                 "image_hw": (480, 640), "n_vox": (96, 96, 96), "thresholds": "STREAM_THRESHOLDS", "stream_len": 16, "panoptic": True},
+    "highres": {"text": "configs[4]: single 18-view 960x720 fragment, 3-level 32/64/128^3 @4cm, GRU fusion (fresh scene), TSDF+occ heads; shipped caps",
+                "metric": "fragments/sec (18x960x720, 3-level 128^3)", "n_views": 18, "image_hw": (720, 960), "n_vox": (128, 128, 128),
+                "thresholds": "HIGHRES_THRESHOLDS", "stream_len": 1, "panoptic": False},
+}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's largest launch: read from the committed ncu export
+TRAFFIC_FILE = os.path.join("profiles", "r02_spconv_hl_ncu_traffic.json")
 
 
 def parse():
@@ -52,6 +65,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fragment", choices=sorted(WORKLOADS))
     return ap.parse_args()
 
 
@@ -179,23 +193,40 @@ def _cpu_threads():
     return max(1, min(os.cpu_count() or 1, 16))
 
 
-def cpu_sample(steps, warmup, max_level=2):
+def workload_cfg(name):
+    """(cfg, fragment kwargs) of a --workload: shipped caps (config/test.yaml:29), thresholds calibrated per workload."""
+    from eprecon_b200 import synth
+    w = WORKLOADS[name]
+    cfg = synth.make_cfg(n_vox=w["n_vox"])
+    cfg.THRESHOLDS = list(getattr(synth, w["thresholds"]))
+    return cfg, {"n_views": w["n_views"], "image_hw": w["image_hw"], "n_vox": w["n_vox"]}
+
+
+def cpu_sample(steps, warmup, max_level=2, workload="fragment"):
     """Oracle (port of the reference algorithm) on the host cores: `steps` full-size fragments through the occupancy
-    initialisation and levels 0..max_level; returns the mean seconds per step."""
+    initialisation and levels 0..max_level; returns the mean seconds per step.  stream16: consecutive fragments of one scene
+    through the recurrent state (TSDF path; the panoptic decoder is not part of the CPU sample)."""
     from oracle import restate
     from eprecon_b200 import synth
     from eprecon_b200.neucon_network import NeuConNet
     torch.set_num_threads(_cpu_threads())
-    cfg = synth.make_cfg()
-    cfg.THRESHOLDS = list(synth.BENCH_THRESHOLDS)
+    cfg, fkw = workload_cfg(workload)
     sd = synth.synthetic_state_dict(NeuConNet(cfg), 1)
-    inputs, fa, fb = synth.make_fragment(seed=1)
+    stream_len = WORKLOADS[workload]["stream_len"]
+    frags = {}
+    state = restate.FusionState()
     times = []
     for it in range(warmup + steps):
-        inputs["scene"] = [f"cpu_scene_{it}"]
+        f = it % stream_len
+        if f not in frags:
+            frags[f] = synth.make_fragment(seed=1, frag_index=f, **fkw)
+        inputs, fa, fb = frags[f]
+        if f == 0:
+            state = restate.FusionState()
+        inputs["scene"] = [f"cpu_scene_{it // stream_len}"]
         t0 = time.perf_counter()
         with torch.no_grad():
-            out = restate.neucon_forward(sd, cfg, fa, fb, inputs, restate.FusionState(), max_level=max_level)
+            out = restate.neucon_forward(sd, cfg, fa, fb, inputs, state, max_level=max_level)
         dt = time.perf_counter() - t0
         assert out is not None
         if it >= warmup:
@@ -216,17 +247,19 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = args.steps, args.warmup
-    probe = cpu_sample(1, 0, max_level=0)          # ~1 s: init stage + level 0
+    wl = getattr(args, "workload", "fragment")
+    probe = cpu_sample(1, 0, max_level=0, workload=wl)          # ~1 s: init stage + level 0
     w = min(warmup, 1)
     lvl = pick_sample_level(probe, steps + w, 300.0)   # keep the whole run within a few minutes
-    t = cpu_sample(steps, w, max_level=lvl)
+    t = cpu_sample(steps, w, max_level=lvl, workload=wl)
     cores = _cpu_threads()
     value = SAMPLE_FRACTION[lvl] / t
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": "fragments/s", "n_gpus": args.gpus,
+    print(json.dumps({"impl": "reference", "metric": WORKLOADS[wl]["metric"], "value": value, "unit": "fragments/s", "n_gpus": args.gpus,
                       "steps": steps, "warmup": w, "ms_per_step": t * 1e3, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": WORKLOAD},
-                      "cpu_baseline": {"value": value, "unit": "fragments/s", "cores": cores, "kind": "port", "sample": SAMPLE_TEXT[lvl],
+                      "config": {"workload": WORKLOADS[wl]["text"]},
+                      "cpu_baseline": {"value": value, "unit": "fragments/s", "cores": cores, "kind": "port",
+                                       "sample": SAMPLE_TEXT[lvl] + PORT_NOTE,
                                        "fragment_fraction_per_step": SAMPLE_FRACTION[lvl], "host_cpus": os.cpu_count()},
                       "e2e": {"value": value, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -298,9 +331,11 @@ class DeviceStage:
 def run_ours(args):
     import queue
 
+    import numpy as np
     import torch.distributed as dist
-    from eprecon_b200 import _lib, ops, synth
+    from eprecon_b200 import _lib, executor, ops, synth
     from eprecon_b200.dist import gather_to_holder, merge_substitute, pack_rows
+    from eprecon_b200.gru_fusion import GRUFusion
     from eprecon_b200.neucon_network import NeuConNet
     from eprecon_b200.streams import FragmentStreams
 
@@ -315,33 +350,60 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     K = args.steps
     S = max(1, int(os.environ.get("EPRECON_STREAMS", str(DEFAULT_STREAMS))))   # fragments in flight per GPU
+    wl_name = args.workload
+    wl = WORKLOADS[wl_name]
+    stream_len = wl["stream_len"]
 
-    cfg = synth.make_cfg()
-    cfg.THRESHOLDS = list(synth.BENCH_THRESHOLDS)
+    cfg, fkw = workload_cfg(wl_name)
     net = NeuConNet(cfg)
     synth.fill_parameters_(net, 1)
     net = net.to(dev)
     net.train()  # the reference evaluates in train mode (main.py:357): batch-statistics BN, training-time caps live
+    net.with_panoptic = bool(wl["panoptic"])
     fs = FragmentStreams(net, S, dev)   # S replicas over the same weights, one host thread + CUDA stream each
+    # configs[2] wires the scene-level fusion behind NeuConNet exactly as models/neuralrecon.py:58-72 does
+    scene_fusers = [GRUFusion(cfg, direct_substitute=True, trianing=False) for _ in range(S)] if wl["panoptic"] else None
 
-    inputs, fa, fb = synth.make_fragment(seed=1)   # every rank / stream: its own copy of the same-shape fragment (weak scaling)
-    host = PackedHost({"inputs": {k: v for k, v in inputs.items() if torch.is_tensor(v) or isinstance(v, list) and torch.is_tensor(v[0])},
-                       "fa": fa, "fb": fb})
-    n_copies = max(4, S + 1)   # rotate over >= 4 resident copies of the inputs: 4 x 54 MB of feature maps > 126 MB L2
-    resident = [host.to_device(dev) for _ in range(n_copies)]
+    # distinct input fragments: 1 (every rank / stream: its own copy of the same-shape fragment, weak scaling) or the 16 of a scene stream
+    hosts = []
+    for f in range(stream_len):
+        inputs, fa, fb = synth.make_fragment(seed=1, frag_index=f, **fkw)
+        hosts.append(PackedHost({"inputs": {k: v for k, v in inputs.items() if torch.is_tensor(v) or isinstance(v, list) and torch.is_tensor(v[0])},
+                                 "fa": fa, "fb": fb}))
+        if f == 0:
+            inputs0 = inputs
+    h2d_bytes = hosts[0].nbytes
+    feat_mb = h2d_bytes / 2 ** 20
+    if stream_len == 1:
+        n_copies = max(4, S + 1)   # rotate over >= 4 resident copies of the inputs: 4 x 54 MB of feature maps > 126 MB L2
+        resident = [hosts[0].to_device(dev) for _ in range(n_copies)]
+    else:
+        n_copies = stream_len      # 16 different fragments x 56 MB >> L2
+        resident = [h.to_device(dev) for h in hosts]
     torch.cuda.synchronize()
-    h2d_bytes = host.nbytes
-    rel = ((inputs["vol_origin_partial"][0] - inputs["vol_origin"][0]) / cfg.VOXEL_SIZE).long()
-    rel_dev = rel.to(dev).to(torch.int32)
-    uid = [0]
+    rel = ((inputs0["vol_origin_partial"][0] - inputs0["vol_origin"][0]) / cfg.VOXEL_SIZE).long()
+    counters = [0] * S
 
-    def fragment(net_r, dev_in, tag):
+    def fragment(net_r, dev_in, tag, slot=0, frag=0, cycle=0):
         ins = dict(dev_in["inputs"])
-        ins["scene"] = [f"scene_r{rank}_{tag}"]   # fresh scene -> GRU state reset -> identical work every fragment
+        if stream_len == 1:
+            ins["scene"] = [f"scene_r{rank}_{tag}"]   # fresh scene -> GRU state reset -> identical work every fragment
+        else:
+            ins["scene"] = [f"scene_r{rank}_s{slot}_c{cycle}"]   # one scene per 16 fragments: the GRU state carries over
         ins["fragment"] = [f"frag_{tag}"]
         out, _ = net_r(dev_in["fa"], dev_in["fb"], ins, {})
-        assert "coords" in out, "forward early-returned (degenerate fragment)"
+        assert "coords" in out, "forward early-returned (degenerate fragment or a cap of config/test.yaml:29 tripped)"
+        if scene_fusers is not None:
+            out = scene_fusers[slot](out["coords"], out["tsdf"], ins, 2, out, save_mesh=(frag == stream_len - 1),
+                                     panoptic_infos=out["panoptic_info"])
         return out
+
+    def body(net_r, slot, k, tag):
+        c = counters[slot]
+        counters[slot] += 1
+        f = c % stream_len
+        src = resident[f] if stream_len > 1 else resident[(k * S + slot) % n_copies]
+        return fragment(net_r, src, tag, slot, f, c // stream_len)
 
     box_lo = [[int(rel[0]) + (rank * S + s) * 24, int(rel[1]), int(rel[2])] for s in range(S)]   # scenes side by side along x
     box_hi = [[lo[0] + cfg.N_VOX[0], lo[1] + cfg.N_VOX[1], lo[2] + cfg.N_VOX[2]] for lo in box_lo]
@@ -364,7 +426,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(n_steps, body):
+    uid = [0]
+
+    def run_steps(n_steps, step_body):
         """Every stream runs `n_steps` fragments back to back (no inter-step barrier); the main thread does the per-step
         exchange when world > 1.  Device-timed between two full synchronisations; returns ms."""
         done = queue.SimpleQueue()
@@ -377,7 +441,7 @@ def run_ours(args):
                 stream.wait_event(e0)
                 for k in range(n_steps):
                     uid[0] += 1
-                    out = body(net_r, slot, k, f"s{slot}_{uid[0]}")
+                    out = step_body(net_r, slot, k, f"s{slot}_{uid[0]}")
                     if world > 1:
                         ev = torch.cuda.Event()
                         ev.record(stream)
@@ -417,25 +481,33 @@ def run_ours(args):
     if rank == 0:
         sampler.start()   # started before the warm-up so that its process start-up stays out of the timed region
     # warm-up: first each replica alone (graph capture, lazily built constant tables), then W concurrent steps
-    fs.warm(lambda net_r, stream: fragment(net_r, resident[0], f"warm{id(net_r)}"))
+    fs.warm(lambda net_r, stream: fragment(net_r, resident[0], f"warm{id(net_r)}", fs.nets.index(net_r), 0, -1))
     W = max(args.warmup, 3)
-    run_steps(W, lambda net_r, slot, k, tag: fragment(net_r, resident[(k * S + slot) % n_copies], tag))
+    run_steps(W, body)
     if rank == 0:
         sampler.rows.clear()   # keep only samples taken under load (timed region + e2e loop)
 
     # ---- timed region: EXACTLY K steps of S fragments each, device-timed, max over ranks
-    ms = run_steps(K, lambda net_r, slot, k, tag: fragment(net_r, resident[(k * S + slot) % n_copies], tag))
+    for s_ in range(S):
+        counters[s_] = 0 if stream_len == 1 else stream_len * ((counters[s_] + stream_len - 1) // stream_len)   # streams start a fresh scene
+    ms = run_steps(K, body)
     value = world * S * K / (ms / 1e3)
 
     # ---- e2e: host (pinned) inputs -> H2D -> forward -> D2H of the sparse TSDF, every fragment, on its own stream
-    stages = [DeviceStage(host, dev) for _ in range(S)]
-    coords_h = [torch.empty((200000, 4), dtype=torch.int64).pin_memory() for _ in range(S)]
-    tsdf_h = [torch.empty((200000, 1), dtype=torch.float32).pin_memory() for _ in range(S)]
+    stage1 = [DeviceStage(hosts[0], dev) for _ in range(S)]   # all fragments of a workload have the same packed layout
+    cap_rows = 200000 if wl_name != "highres" else 400000
+    coords_h = [torch.empty((cap_rows, 4), dtype=torch.int64).pin_memory() for _ in range(S)]
+    tsdf_h = [torch.empty((cap_rows, 1), dtype=torch.float32).pin_memory() for _ in range(S)]
     d2h = [0]
 
     def e2e_fragment(net_r, slot, k, tag):
-        dev_in = stages[slot].load()   # one pinned->device copy per dtype (fp32 features/matrices, bool GT occupancy)
-        o = fragment(net_r, dev_in, tag)
+        c = counters[slot]
+        counters[slot] += 1
+        f = c % stream_len
+        st = stage1[slot]
+        st.host = hosts[f]             # the step's own fragment: one pinned->device copy per dtype (fp32 features/matrices, bool GT occupancy)
+        dev_in = st.load()
+        o = fragment(net_r, dev_in, tag, slot, f, c // stream_len)
         n = o["coords"].shape[0]
         coords_h[slot][:n].copy_(o["coords"], non_blocking=True)
         tsdf_h[slot][:n].copy_(o["tsdf"], non_blocking=True)
@@ -443,139 +515,155 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()   # the caller holds the result on the host before the next fragment
         return o
 
+    for s_ in range(S):
+        counters[s_] = stream_len * ((counters[s_] + stream_len - 1) // stream_len)
     run_steps(1, e2e_fragment)
+    for s_ in range(S):
+        counters[s_] = stream_len * ((counters[s_] + stream_len - 1) // stream_len)
     ms_e2e = run_steps(K, e2e_fragment)
     e2e_value = world * S * K / (ms_e2e / 1e3)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- single-stream pass on the main thread: latency of one fragment, per-launch CUDA-event durations of the two
-    #      dominant kernel families (events around every launch would perturb the multi-stream timed region, and a
-    #      kernel sharing the SMs with other streams has no roofline of its own), launch count, algorithmic work
+    #      dominant kernel families (a kernel sharing the SMs with other streams has no roofline of its own), launch count,
+    #      algorithmic work.  The conv events are recorded INSIDE the native executor (ep_exec_profile_*: event record and
+    #      launch are issued back to back from C++, no host gap); the back-projection is one launch per call from Python.
     roofline = None
     kernel_share = {}
     single = None
     launches_per_fragment = None
     if rank == 0:
         net0 = fs.nets[0]
-        for w in range(2):
-            fragment(net0, resident[w], f"single_warm{w}")
+        L = _lib.lib()
+        counters[0] = stream_len * ((counters[0] + stream_len - 1) // stream_len)
+        for w in range(2 if stream_len == 1 else stream_len):
+            body(net0, 0, w, f"single_warm{w}")
         torch.cuda.synchronize()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         evs[0].record()
         for k in range(K):
-            fragment(net0, resident[k % n_copies], f"single{k}")
+            body(net0, 0, k, f"single{k}")
             evs[k + 1].record()
         torch.cuda.synchronize()
         per = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(K))
-        single_ms = per[len(per) // 2]      # median: this pass is host-bound (884 launches from one thread) and jittery
+        single_ms = per[len(per) // 2]
         single = {"ms_per_fragment": single_ms, "fragments_per_s": 1e3 / single_ms, "ms_min": per[0], "ms_max": per[-1],
-                  "note": "one fragment at a time on one stream (latency view of the same step; median of K, host-bound)"}
-        # launch count of one fragment on the shipped (native-executor) path
+                  "note": "one fragment at a time on one stream (latency view of the same step; median of K)"}
         # launch count of one steady-state fragment; cudaProfilerStart/Stop bracket exactly this fragment, so that
         # `ncu --profile-from-start off ... python bench.py` lists one fragment of this very command (profiles/README.md)
+        counters[0] = stream_len * ((counters[0] + stream_len - 1) // stream_len)
         _lib.LAUNCHES["n"] = 0
         torch.cuda.profiler.start()
-        fragment(net0, resident[0], "count")
+        body(net0, 0, 0, "count")
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         launches_per_fragment = _lib.LAUNCHES["n"]
-        # per-launch events need the per-kernel Python programs (the native executor issues the very same launches
-        # from C++, where bench.py cannot bracket them): same kernels, same arguments, same order
-        from eprecon_b200 import executor
-        exec_was, executor.ENABLED = executor.ENABLED, False
-        fragment(net0, resident[1], "prof_warm")
-        ops.PROFILE = {"mode": "events"}
-        for k in range(K):
-            fragment(net0, resident[k % n_copies], f"prof{k}")
-        torch.cuda.synchronize()
-        prof_ms = single_ms * K
-        prof, ops.PROFILE = ops.PROFILE, {"mode": "work"}
-        fragment(net0, resident[0], "work")
-        work, ops.PROFILE = ops.PROFILE, None
-        executor.ENABLED = exec_was
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        fam = {}
-        for kind in ("spconv", "bp_gather"):
-            evs = prof.get(kind, [])
-            tot_ms = sum(a.elapsed_time(b) for a, b in evs)
-            fam[kind] = {"launches": len(evs), "ms": tot_ms}
-            kernel_share[kind] = {"launches_per_fragment": len(evs) // max(K, 1), "ms_per_fragment": tot_ms / K,
-                                  "share_of_single_stream_step": tot_ms / prof_ms if prof_ms else None}
-        per_step = len(work.get("spconv_work", []))
+        # per-launch profile over K fragments: conv family from the executor's own events, back-projection from ops.PROFILE
+        counters[0] = stream_len * ((counters[0] + stream_len - 1) // stream_len)
+        ops.PROFILE = {"mode": "events"}
+        _lib.check(L.ep_exec_profile_enable(1), "ep_exec_profile_enable")
+        for k in range(K):
+            body(net0, 0, k, f"prof{k}")
+        torch.cuda.synchronize()
+        cap = 4096
+        meta = np.zeros((cap, 7), dtype=np.int64)
+        cms = np.zeros(cap, dtype=np.float32)
+        n_rec = L.ep_exec_profile_collect(meta.ctypes.data, cms.ctypes.data, cap)
+        assert n_rec > 0, "the native executor recorded no sparse-conv launch (EPRECON_EXEC=0?)"
+        meta, cms = meta[:n_rec], cms[:n_rec]
+        prof, ops.PROFILE = ops.PROFILE, {"mode": "work"}
+        counters[0] = stream_len * ((counters[0] + stream_len - 1) // stream_len)
+        body(net0, 0, 0, "work")
+        work, ops.PROFILE = ops.PROFILE, None
+        per_step = n_rec // K
+        bp_evs = prof.get("bp_gather", [])
+        bp_ms = sum(a.elapsed_time(b) for a, b in bp_evs) / K
+        sp_ms = float(cms.sum()) / K
+        kk, cin, cout, m_in, m_out, pairs, impl = (meta[:, i].astype(np.float64) for i in range(7))
+        flops = float((2.0 * cin * cout * pairs).sum()) / K
+        sp_bytes = float((4.0 * (m_in * cin + m_out * cout + kk * cin * cout + pairs)).sum()) / K
+        gather_bytes = float((pairs * np.ceil(cin / 32.0) * 128.0)[impl == 2].sum()) / K     # half-pair rows the TMA unit fetches
+        tc = impl > 0
+        kernel_share["spconv"] = {"launches_per_fragment": per_step, "ms_per_fragment": sp_ms,
+                                  "share_of_single_stream_step": sp_ms / single_ms,
+                                  "tensor_core_launches": int(tc.sum()) // K, "tensor_core_ms": float(cms[tc].sum()) / K,
+                                  "linear_k1_launches": int((~tc).sum()) // K, "linear_k1_ms": float(cms[~tc].sum()) / K}
+        kernel_share["bp_gather"] = {"launches_per_fragment": len(bp_evs) // max(K, 1), "ms_per_fragment": bp_ms,
+                                     "share_of_single_stream_step": bp_ms / single_ms}
         dump = os.environ.get("EPRECON_BENCH_DUMP")
-        if dump and per_step and len(prof.get("spconv", [])) == per_step * K:
-            # per-launch view of the sparse-conv family: algorithmic work next to the mean CUDA-event duration
-            evs = prof["spconv"]
+        if dump and per_step * K == n_rec:
             with open(dump, "w") as f:
-                for j, w in enumerate(work["spconv_work"]):
-                    us = 1e3 * sum(evs[k * per_step + j][0].elapsed_time(evs[k * per_step + j][1]) for k in range(K)) / K
-                    f.write(json.dumps(dict(w, us=round(us, 2), impl="ffma" if w["K"] == 1 else ops.SPCONV_IMPL)) + "\n")
-        flops = sum(2.0 * w["cin"] * w["cout"] * w["pairs"] for w in work.get("spconv_work", []))
-        sp_bytes = sum(4.0 * (w["m_in"] * w["cin"] + w["m_out"] * w["cout"] + w["K"] * w["cin"] * w["cout"] + w["pairs"])
-                       for w in work.get("spconv_work", []))
+                for j in range(per_step):
+                    us = 1e3 * float(cms[j::per_step].mean())
+                    f.write(json.dumps({"K": int(meta[j, 0]), "cin": int(meta[j, 1]), "cout": int(meta[j, 2]), "m_in": int(meta[j, 3]),
+                                        "m_out": int(meta[j, 4]), "pairs": int(meta[j, 5]),
+                                        "impl": {0: "ffma", 1: "tf32x3", 2: "hl"}[int(meta[j, 6])], "us": round(us, 2)}) + "\n")
         bp_bytes = sum(w["bytes"] for w in work.get("bp_gather_work", []))
-        sp_ms = fam["spconv"]["ms"] / K
-        bp_ms = fam["bp_gather"]["ms"] / K
         tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         src = "of measured (MEASURED_PEAKS.json)" if peaks else "of fallback (B200_PROFILING.md)"
-        where = ("per-launch CUDA events on the launching stream over K single-stream fragments run right after the timed "
-                 "region (same step, same inputs; launches issued by the per-kernel Python programs so that each one can "
-                 "be bracketed); shares are relative to the single-stream step of the shipped path")
-        if sp_ms >= bp_ms:
-            ach = flops / (sp_ms * 1e-3) / 1e12 if sp_ms else 0.0
-            impl = ops.SPCONV_IMPL
-            kname = {"tf32x3": "spconv_tc_kernel<3> (gather -> tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators)",
-                     "tf32": "spconv_tc_kernel<1> (gather -> tcgen05.mma kind::tf32)",
-                     "ffma": "spconv_kernel (gather-GEMM, fp32 FFMA)"}[impl]
-            roofline = {"kernel": kname + "; K=1 linears run on spconv_kernel (fp32 FFMA)", "bound": "tensor", "achieved": ach,
-                        "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak,
-                        "traffic": SPCONV_TRAFFIC["bytes"] if impl != "ffma" else None,
-                        "traffic_note": SPCONV_TRAFFIC["note"], "measured": where,
-                        "peak_source": src + ", bf16 dense sustained (tf32 dense peak is half of it); achieved counts the "
-                                             "algorithmic 2*Cin*Cout*pairs flops once (3xTF32 issues 3 MMAs per product); the kernel is "
-                                             "gather/L2-bound, see memory_view",
-                        "memory_view": {"achieved_GBs": sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms else None, "peak_GBs": hbm_peak,
-                                        "frac": (sp_bytes / (sp_ms * 1e-3) / 1e9 / hbm_peak) if sp_ms else None,
-                                        "bytes": "4(M_in*Cin + M_out*Cout) + 4*K*Cin*Cout + 4*pairs per launch (lower bound: every input row read once)"},
-                        "launches_per_fragment": per_step, "algorithmic_flops_per_fragment": flops,
-                        "algorithmic_bytes_per_fragment": sp_bytes, "avg_launch_us": 1e3 * sp_ms / max(per_step, 1)}
-        else:
-            ach = bp_bytes / (bp_ms * 1e-3) / 1e9 if bp_ms else 0.0
-            roofline = {"kernel": "bp_fused_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "peak_source": src, "measured": where,
-                        "algorithmic_bytes_per_fragment": bp_bytes}
+        where = ("CUDA events recorded inside the native executor around every sparse-conv launch (operand split + conv + split-K "
+                 "reduce), on the launching stream, over K single-stream fragments run right after the timed region (same step, "
+                 "same inputs, the shipped path); shares are relative to the single-stream step")
+        traffic, traffic_note = None, f"no committed ncu export at {TRAFFIC_FILE}"
+        try:
+            tj = json.load(open(os.path.join(ROOT, TRAFFIC_FILE)))
+            traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
+            traffic_note = f"{TRAFFIC_FILE}: {tj.get('launch', '')} (algorithmic bytes of that launch: {tj.get('algorithmic_bytes')})"
+        except Exception:
+            pass
+        impl_name = ops.SPCONV_IMPL
+        kname = {"hl": "spconv_hl_kernel (TMA tile::gather4 of pre-split half-pair rows -> tcgen05.mma kind::f16, fp32 TMEM accumulators)",
+                 "tf32x3": "spconv_tc_kernel<3> (register gather -> tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators)",
+                 "tf32": "spconv_tc_kernel<1> (gather -> tcgen05.mma kind::tf32)",
+                 "ffma": "spconv_kernel (gather-GEMM, fp32 FFMA)"}[impl_name]
+        ach = flops / (sp_ms * 1e-3) / 1e12 if sp_ms else 0.0
+        roofline = {"kernel": kname + "; K=1 linears run on spconv_kernel (fp32 FFMA)", "bound": "tensor", "achieved": ach,
+                    "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak, "traffic": traffic, "traffic_note": traffic_note,
+                    "measured": where,
+                    "peak_source": src + ", bf16 dense sustained; achieved counts the algorithmic 2*Cin*Cout*pairs flops once (the "
+                                         "split operands issue 3 MMAs per product); the kernel is bound by the L2 -> SM gather, see memory_view",
+                    "memory_view": {"achieved_GBs": sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms else None, "peak_GBs": hbm_peak,
+                                    "frac": (sp_bytes / (sp_ms * 1e-3) / 1e9 / hbm_peak) if sp_ms else None,
+                                    "bytes": "4(M_in*Cin + M_out*Cout) + 4*K*Cin*Cout + 4*pairs per launch (lower bound: every input row read once)",
+                                    "gathered_bytes_per_fragment": gather_bytes,
+                                    "gather_GBs": gather_bytes / (float(cms[impl == 2].sum()) / K * 1e-3) / 1e9 if (impl == 2).any() else None},
+                    "launches_per_fragment": per_step, "algorithmic_flops_per_fragment": flops,
+                    "algorithmic_bytes_per_fragment": sp_bytes, "avg_launch_us": 1e3 * sp_ms / max(per_step, 1)}
         roofline["back_projection"] = {"achieved_GBs": bp_bytes / (bp_ms * 1e-3) / 1e9 if bp_ms else None, "peak_GBs": hbm_peak,
                                        "frac": (bp_bytes / (bp_ms * 1e-3) / 1e9 / hbm_peak) if bp_ms else None,
                                        "algorithmic_bytes_per_fragment": bp_bytes, "ms_per_fragment": bp_ms}
-        try:
-            roofline["back_projection"]["batched"] = bp_batched_probe(dev, inputs, peaks)
-        except Exception as ex:   # the probe must never take the bench line down
-            roofline["back_projection"]["batched"] = {"error": repr(ex)}
+        if wl_name == "fragment":
+            try:
+                roofline["back_projection"]["batched"] = bp_batched_probe(dev, inputs0, peaks)
+            except Exception as ex:   # the probe must never take the bench line down
+                roofline["back_projection"]["batched"] = {"error": repr(ex)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not os.environ.get("EPRECON_BENCH_SKIP_CPU"):
-        probe = cpu_sample(1, 0, max_level=0)
+        probe = cpu_sample(1, 0, max_level=0, workload=wl_name)
         lvl = pick_sample_level(probe, 1, 60.0)      # one step of ~20 s on 8-16 cores: the full fragment
-        t = cpu_sample(1, 0, max_level=lvl)
+        t = cpu_sample(1, 0, max_level=lvl, workload=wl_name)
         cpu_baseline = {"value": SAMPLE_FRACTION[lvl] / t, "unit": "fragments/s", "cores": _cpu_threads(), "host_cpus": os.cpu_count(),
-                        "kind": "port", "sample": SAMPLE_TEXT[lvl] + f"; {t:.1f} s of CPU work",
+                        "kind": "port", "sample": SAMPLE_TEXT[lvl] + f"; {t:.1f} s of CPU work" + PORT_NOTE,
                         "fragment_fraction_per_step": SAMPLE_FRACTION[lvl]}
 
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "fragments/s", "n_gpus": world, "steps": K,
+            "metric": wl["metric"], "value": value, "unit": "fragments/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "fragments_per_step": S * world,
+            "config": {"workload": wl["text"], "fragments_per_step": S * world,
                        "streams_per_gpu": S, "step": f"{S} independent fragments in flight per GPU (one CUDA stream + host thread each, "
                                                      "shared weights); value = fragments completed / device time",
-                       "sizes": fs.nets[0].last_sizes, "thresholds": cfg.THRESHOLDS,
-                       "l2": f"inputs rotated over {n_copies} HBM-resident copies ({n_copies * 54} MB of feature maps > 126 MB L2)",
+                       "sizes": fs.nets[0].last_sizes, "thresholds": cfg.THRESHOLDS, "caps": cfg.TRAIN_NUM_SAMPLE,
+                       "operands": "sparse-conv operands are fp16 pairs h + l*2^-11 (22 significant bits, as 3xTF32), fp32 accumulation" if ops.SPCONV_IMPL == "hl" else ops.SPCONV_IMPL,
+                       "l2": f"inputs rotated over {n_copies} HBM-resident fragments ({n_copies * feat_mb:.0f} MB of feature maps > 126 MB L2)",
                        "multi_gpu": (f"{S} fragments per rank per step + NCCL send/recv of the step's sparse TSDF rows to the holder (rank 0) + one merge "
                                      "kernel there" + (" [EXCHANGE DISABLED: diagnostic run]" if skip_exchange else "")) if world > 1 else "n/a"},
             "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": h2d_bytes * S, "d2h_bytes_per_step": d2h[0] * S,

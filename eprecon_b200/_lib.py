@@ -45,7 +45,7 @@ KERNELS_PER_CALL = {"ep_version": 0, "ep_backproject_workspace_bytes": 0, "ep_co
                     "ep_compact_flags": 3, "ep_sort_segments": 12, "ep_hash_build": 2,
                     # native executor calls report their own launch count (executor.py adds it)
                     "ep_masked_attention_workspace_bytes": 0, "ep_masked_attention": 2,
-                    "ep_exec_launch_count": 0, "ep_exec_desc_check": 0, "ep_exec_spvcnn": 0, "ep_exec_gru_level": 0, "ep_exec_linear4x": 0,
+                    "ep_exec_launch_count": 0, "ep_exec_profile_enable": 0, "ep_exec_profile_collect": 0, "ep_exec_desc_check": 0, "ep_exec_spvcnn": 0, "ep_exec_gru_level": 0, "ep_exec_linear4x": 0,
                     "ep_exec_init_head": 0}
 LAUNCHES = {"n": 0}
 

@@ -17,12 +17,28 @@
 
 #include <atomic>
 #include <cstring>
+#include <vector>
 
 #include "eprecon_b200.h"
 
 namespace {
 
 std::atomic<size_t> g_launches{0};
+
+// ---- per-launch profiling of the sparse-conv family (bench.py's roofline): when enabled on the calling host thread,
+// every spconv() brackets its launches with a CUDA-event pair recorded on the executor's stream (no host gap between
+// the record and the launch it brackets: both are issued from this C++ code) and counts the valid neighbour pairs.
+struct ProfRec { cudaEvent_t e0, e1; int K, cin, cout, m_in, m_out, impl; int* pairs_dev; };
+struct Prof { std::vector<ProfRec> recs; int* pairs_pool = nullptr; int pool_used = 0; };
+constexpr int kProfPool = 4096;
+thread_local Prof* tl_prof = nullptr;
+
+__global__ void count_valid_kernel(const int* __restrict__ nbr, long long n, int* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ok = (i < n && nbr[i] >= 0) ? 1 : 0;
+  const unsigned b = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
+}
 
 __global__ void csr_expand_kernel(const uint64_t* __restrict__ keys_sorted, const int* __restrict__ seg_start,
                                   const int* __restrict__ seg_end, int s, int* __restrict__ s0, int* __restrict__ s1) {
@@ -283,6 +299,20 @@ Mat spconv(Exec& e, const float* x, int ldx, int m_in, const Conv& cv, const int
   }
   float* pp = nullptr;
   if (part) { pp = alloc<float>(e, (size_t)ep_spconv_num_row_tiles(m_out) * 2 * cv.cout); *part = pp; }
+  ProfRec* rec = nullptr;
+  if (tl_prof && !e.err && tl_prof->pool_used < kProfPool) {
+    ProfRec r{};
+    r.K = cv.K; r.cin = cv.cin; r.cout = cv.cout; r.m_in = m_in; r.m_out = m_out;
+    r.impl = cv.K == 1 ? 0 : (cv.w_hl ? 2 : 1);
+    r.pairs_dev = tl_prof->pairs_pool + tl_prof->pool_used++;
+    if (nbr) count_valid_kernel<<<ep_div_up((long long)m_out * cv.K, 256), 256, 0, e.st>>>(nbr, (long long)m_out * cv.K, r.pairs_dev);
+    if (cudaEventCreate(&r.e0) == cudaSuccess && cudaEventCreate(&r.e1) == cudaSuccess) {
+      cudaEventRecord(r.e0, e.st);
+      tl_prof->recs.push_back(r);
+      rec = &tl_prof->recs.back();
+    }
+  }
+  struct ProfEnd { ProfRec* r; cudaStream_t st; ~ProfEnd() { if (r) cudaEventRecord(r->e1, st); } } prof_end{rec, e.st};
   if (cv.K == 1) {
     RUN(e, 1, ep_spconv_fwd(x, ldx, cv.cin, nbr, 1, cv.w, c4, cv.cout, cv.bias, o.p, o.ld, m_out, pp, e.st));
   } else if (cv.w_hl) {
@@ -469,6 +499,54 @@ inline int finish(Exec& e, int64_t* stats) {
 extern "C" {
 
 size_t ep_exec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// Per-launch profiling of the sparse-conv family for the CALLING host thread (see ProfRec).  enable(1) starts recording,
+// collect() synchronises the recorded events and returns up to `cap` records: meta[i] = {K, cin, cout, m_in, m_out, pairs,
+// impl (0 FFMA linear, 1 3xTF32, 2 half-pair TMA)}, ms[i] = device time between the bracketing events; recording stops.
+int ep_exec_profile_enable(int on) {
+  if (on) {
+    if (!tl_prof) tl_prof = new Prof();
+    if (!tl_prof->pairs_pool && cudaMalloc((void**)&tl_prof->pairs_pool, kProfPool * sizeof(int)) != cudaSuccess) return EP_ERR_CUDA;
+    if (cudaMemset(tl_prof->pairs_pool, 0, kProfPool * sizeof(int)) != cudaSuccess) return EP_ERR_CUDA;
+    tl_prof->pool_used = 0;
+    for (auto& r : tl_prof->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    tl_prof->recs.clear();
+    tl_prof->recs.reserve(kProfPool);
+  } else if (tl_prof) {
+    for (auto& r : tl_prof->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    if (tl_prof->pairs_pool) cudaFree(tl_prof->pairs_pool);
+    delete tl_prof;
+    tl_prof = nullptr;
+  }
+  return EP_OK;
+}
+
+int ep_exec_profile_collect(int64_t* meta, float* ms, int cap) {
+  if (!tl_prof || !meta || !ms) return EP_ERR_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return EP_ERR_CUDA;
+  std::vector<int> pairs(kProfPool, 0);
+  if (cudaMemcpy(pairs.data(), tl_prof->pairs_pool, kProfPool * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return EP_ERR_CUDA;
+  int n = 0;
+  for (auto& r : tl_prof->recs) {
+    if (n < cap) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, r.e0, r.e1);
+      const int idx = (int)(r.pairs_dev - tl_prof->pairs_pool);
+      int64_t* m = meta + 7 * (size_t)n;
+      m[0] = r.K; m[1] = r.cin; m[2] = r.cout; m[3] = r.m_in; m[4] = r.m_out;
+      m[5] = r.K == 1 ? r.m_out : pairs[idx];
+      m[6] = r.impl;
+      ms[n] = t;
+      ++n;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  tl_prof->recs.clear();
+  const int ret = n;
+  ep_exec_profile_enable(0);
+  return ret;
+}
 
 // Host-only: parse a descriptor exactly as the executor would (kind 0 SPVCNN, 1 GRU level, 2 Linear4x, 3 init head) and
 // return the number of int64 words consumed, or EP_ERR_ARG on a layout / shape mismatch.  Needs no GPU.

@@ -212,3 +212,9 @@ BENCH_THRESHOLDS = [-1.666, -0.471, -0.39]
 # 373 k candidates) would trip the shipped 1.5 x 120 000 cap (config/test.yaml:29; neucon_network.py:469-475).  Calibrated
 # on the CPU oracle (seed-1 weights / fragment): 6 968 / 46 649 / 109 439 occupied voxels, all inside the shipped caps.
 HIGHRES_THRESHOLDS = [-1.666, -0.471, -0.17]
+
+# BASELINE configs[2] (16 overlapping fragments of one scene, GRU fusion across fragments): the fused level-2 set (current
+# fragment + the scene state inside its volume) must stay inside the shipped 1.5 x 120 000 cap for every fragment of the
+# stream, so fewer voxels may survive per fragment than in the single-fragment workload.  Calibrated on the GPU path with
+# tools/calibrate_stream.py (seed-1 weights / fragments 0..15).
+STREAM_THRESHOLDS = [-1.666, -0.471, -0.39]

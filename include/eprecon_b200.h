@@ -214,6 +214,10 @@ int ep_translate_index(const int32_t* idx, int64_t n, const int32_t* rank, int32
  *   ep_exec_init_head  <- Occupancy_Initialization.forward sparse head (models/occupancy_initialization.py:131-176) */
 size_t ep_exec_launch_count(void);
 int ep_exec_desc_check(int kind, const int64_t* desc);   /* host-only descriptor validation, no GPU needed */
+/* per-launch CUDA-event timing of the sparse-conv family inside the executor (calling host thread only): enable(1), run
+ * fragments, collect() -> number of records; meta int64 [cap,7] = {K, cin, cout, m_in, m_out, valid pairs, impl}, ms [cap]. */
+int ep_exec_profile_enable(int on);
+int ep_exec_profile_collect(int64_t* meta, float* ms, int cap);
 int ep_exec_spvcnn(const int64_t* desc, const int64_t* globals, const float* pts, const float* feat, int ld_feat,
                    int64_t n, float vres, float* out, int ld_out, void* arena, size_t arena_bytes, int64_t* stats,
                    cudaStream_t stream);

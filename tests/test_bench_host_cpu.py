@@ -41,7 +41,8 @@ def test_cpu_sample_level_fits_the_budget():
 def test_reference_arm_json_contract(monkeypatch):
     calls = []
 
-    def fake_sample(steps, warmup, max_level=2):
+    def fake_sample(steps, warmup, max_level=2, workload="fragment"):
+        assert workload == "fragment"
         calls.append((steps, warmup, max_level))
         return {0: 0.5, 1: 1.4, 2: 9.0}[max_level]
     monkeypatch.setattr(bench, "cpu_sample", fake_sample)
