@@ -167,7 +167,7 @@ struct VoxelSet { int32_t* coords; int m; int stride; Table t; int32_t* k3; };
 struct Csr { const int32_t* perm; const int32_t* s0; const int32_t* s1; int m; };
 struct Seg { uint64_t* ks; int32_t* perm; int32_t* s0; int32_t* s1; int32_t* soi; int S; };
 struct PointCloud { int n; float* scaled; Csr csr1; VoxelSet vox; int32_t* tap_idx[3]; float* tap_w[3]; };
-struct Mat { float* p; int ld; };
+struct Mat { float* p; int ld; uint16_t* hl; };   // hl: half-pair copy of the rows (csrc/spconv_hl.cu) or nullptr
 
 Table make_table(Exec& e, const int32_t* coords, int m, int batch_first) {
   uint64_t* keys = alloc<uint64_t>(e, m);
@@ -271,15 +271,20 @@ Csr csr_for(Exec& e, PointCloud& pc, const VoxelSet& v) {
 }
 
 // ------------------------------------------------------------------------------------------------------ dense math
-Mat voxelize(Exec& e, const Csr& csr, const float* feat, int ld, int c) {
-  Mat o{alloc<float>(e, (size_t)csr.m * ceil4(c)), ceil4(c)};
-  RUN(e, 1, ep_segment_mean(feat, ld, c, csr.perm, csr.s0, csr.s1, csr.m, o.p, o.ld, e.st));
+Mat voxelize(Exec& e, const Csr& csr, const float* feat, int ld, int c, bool want_hl = false) {
+  Mat o{alloc<float>(e, (size_t)csr.m * ceil4(c)), ceil4(c), nullptr};
+  if (want_hl) {   // the mean-pooled rows feed a tensor-core conv: write their half-pair copy in the same pass
+    o.hl = alloc<uint16_t>(e, (size_t)csr.m * ep_hl_slabs(c) * 64);
+    RUN(e, 1, ep_hl_segment_mean(feat, ld, c, csr.perm, csr.s0, csr.s1, csr.m, o.p, o.ld, o.hl, nullptr, e.st));
+  } else {
+    RUN(e, 1, ep_segment_mean(feat, ld, c, csr.perm, csr.s0, csr.s1, csr.m, o.p, o.ld, e.st));
+  }
   return o;
 }
 
 Mat devoxelize(Exec& e, const Mat& v, int c, const int32_t* idx, const float* w, int n, const float* add, int ld_add,
                float* out = nullptr, int ld_out = 0) {
-  Mat o{out, ld_out};
+  Mat o{out, ld_out, nullptr};
   if (!out) { o.p = alloc<float>(e, (size_t)n * ceil4(c)); o.ld = ceil4(c); }
   RUN(e, 1, ep_devoxelize(v.p, v.ld, c, idx, w, n, add, ld_add, o.p, o.ld, e.st));
   return o;
@@ -289,9 +294,9 @@ Mat devoxelize(Exec& e, const Mat& v, int c, const int32_t* idx, const float* w,
 // gather kernel on half-pair operands (csrc/spconv_hl.cu; the input's m_in rows are split right here) when the descriptor
 // carries w_hl, else the round-1 3xTF32 kernel
 Mat spconv(Exec& e, const float* x, int ldx, int m_in, const Conv& cv, const int32_t* nbr, int m_out, float** part,
-           float* out = nullptr, int ld_out = 0) {
+           float* out = nullptr, int ld_out = 0, const uint16_t* x_hl = nullptr) {
   const int c4 = ceil4(cv.cout);
-  Mat o{out, ld_out};
+  Mat o{out, ld_out, nullptr};
   if (!out) {
     o.p = alloc<float>(e, (size_t)m_out * c4);
     o.ld = c4;
@@ -317,8 +322,12 @@ Mat spconv(Exec& e, const float* x, int ldx, int m_in, const Conv& cv, const int
     RUN(e, 1, ep_spconv_fwd(x, ldx, cv.cin, nbr, 1, cv.w, c4, cv.cout, cv.bias, o.p, o.ld, m_out, pp, e.st));
   } else if (cv.w_hl) {
     const size_t mark = e.off;
-    uint16_t* xs = alloc<uint16_t>(e, (size_t)m_in * ep_hl_slabs(cv.cin) * 64);
-    RUN(e, 1, ep_hl_split_rows(x, ldx, cv.cin, m_in, xs, nullptr, e.st));
+    const uint16_t* xs = x_hl;
+    if (!xs) {      // no producer wrote the half-pair copy (concat buffers, column slices): split here
+      uint16_t* t = alloc<uint16_t>(e, (size_t)m_in * ep_hl_slabs(cv.cin) * 64);
+      RUN(e, 1, ep_hl_split_rows(x, ldx, cv.cin, m_in, t, nullptr, e.st));
+      xs = t;
+    }
     const size_t wsb = ep_spconv_hl_workspace_bytes(m_out, cv.npad, cv.K);
     void* ws = wsb ? (void*)alloc<char>(e, wsb) : nullptr;
     RUN(e, wsb ? 2 : 1, ep_spconv_hl_fwd(xs, m_in, cv.cin, nbr, cv.K, cv.w_hl, cv.npad, cv.cout, cv.bias, o.p, o.ld, m_out, pp, ws,
@@ -341,12 +350,23 @@ float* bn_ss(Exec& e, const float* part, int m, const Norm& bn) {
   return ss;
 }
 
-Mat conv_bn_relu(Exec& e, const float* x, int ldx, int m_in, const int32_t* nbr, const Conv& cv, const Norm& bn, int m_out,
-                 float* out = nullptr, int ld_out = 0) {
+// BatchNorm apply (+ residual b, + ReLU) in place; with want_hl the same pass writes the rows' half-pair copy for the next conv
+void bn_apply(Exec& e, Mat& y, const float* ss, const float* b, int ld_b, const float* ss_b, int m, int c, bool want_hl) {
+  if (want_hl) {
+    y.hl = alloc<uint16_t>(e, (size_t)m * ep_hl_slabs(c) * 64);
+    RUN(e, 1, ep_hl_affine_act(y.p, y.ld, ss, b, ld_b, ss_b, 1, m, c, y.p, y.ld, y.hl, nullptr, e.st));
+  } else {
+    RUN(e, 1, ep_affine_act(y.p, y.ld, ss, b, ld_b, ss_b, 1, m, c, y.p, y.ld, e.st));
+  }
+}
+
+// want_hl: the result feeds a K > 1 conv of a descriptor in half-pair mode (the caller checks the consumer's w_hl)
+Mat conv_bn_relu(Exec& e, const Mat& x, int m_in, const int32_t* nbr, const Conv& cv, const Norm& bn, int m_out,
+                 float* out = nullptr, int ld_out = 0, bool want_hl = false) {
   float* part = nullptr;
-  Mat y = spconv(e, x, ldx, m_in, cv, nbr, m_out, &part, out, ld_out);
+  Mat y = spconv(e, x.p, x.ld, m_in, cv, nbr, m_out, &part, out, ld_out, x.hl);
   const float* ss = bn_ss(e, part, m_out, bn);
-  RUN(e, 1, ep_affine_act(y.p, y.ld, ss, nullptr, 0, nullptr, 1, m_out, cv.cout, y.p, y.ld, e.st));
+  bn_apply(e, y, ss, nullptr, 0, nullptr, m_out, cv.cout, want_hl);
   return y;
 }
 
@@ -360,18 +380,19 @@ ResBlock read_res(Reader& r) {
   return b;
 }
 
-Mat residual_block(Exec& e, const Mat& x, const int32_t* nbr, const ResBlock& b, int m) {
-  Mat t = conv_bn_relu(e, x.p, x.ld, m, nbr, b.c1, b.b1, m);
+Mat residual_block(Exec& e, const Mat& x, const int32_t* nbr, const ResBlock& b, int m, bool want_hl) {
+  const bool hl = b.c2.w_hl != nullptr;
+  Mat t = conv_bn_relu(e, x, m, nbr, b.c1, b.b1, m, nullptr, 0, hl);
   float* part_u = nullptr;
-  Mat u = spconv(e, t.p, t.ld, m, b.c2, nbr, m, &part_u);
+  Mat u = spconv(e, t.p, t.ld, m, b.c2, nbr, m, &part_u, nullptr, 0, t.hl);
   const float* ss_u = bn_ss(e, part_u, m, b.b2);
   if (!b.has_down) {
-    RUN(e, 1, ep_affine_act(u.p, u.ld, ss_u, x.p, x.ld, nullptr, 1, m, b.c2.cout, u.p, u.ld, e.st));
+    bn_apply(e, u, ss_u, x.p, x.ld, nullptr, m, b.c2.cout, want_hl && hl);
   } else {
     float* part_d = nullptr;
     Mat d = spconv(e, x.p, x.ld, m, b.cd, nullptr, m, &part_d);
     const float* ss_d = bn_ss(e, part_d, m, b.bd);
-    RUN(e, 1, ep_affine_act(u.p, u.ld, ss_u, d.p, d.ld, ss_d, 1, m, b.c2.cout, u.p, u.ld, e.st));
+    bn_apply(e, u, ss_u, d.p, d.ld, ss_d, m, b.c2.cout, want_hl && hl);
   }
   return u;
 }
@@ -390,8 +411,8 @@ struct SConv { Conv conv; Conv lin; };
 
 Mat sconv3d(Exec& e, const SConv& s, const float* feat, int ldf, int n, PointCloud& pc, const Globals& G,
             const int32_t* tap_idx, const float* tap_w) {
-  Mat x = voxelize(e, pc.csr1, feat, ldf, s.conv.cin);
-  Mat y = spconv(e, x.p, x.ld, pc.vox.m, s.conv, kmap_k3(e, pc.vox, G), pc.vox.m, nullptr);
+  Mat x = voxelize(e, pc.csr1, feat, ldf, s.conv.cin, s.conv.w_hl != nullptr);
+  Mat y = spconv(e, x.p, x.ld, pc.vox.m, s.conv, kmap_k3(e, pc.vox, G), pc.vox.m, nullptr, nullptr, 0, x.hl);
   Mat lin = spconv(e, feat, ldf, n, s.lin, nullptr, n, nullptr);
   return devoxelize(e, y, s.conv.cout, tap_idx, tap_w, n, lin.p, lin.ld);
 }
@@ -401,12 +422,12 @@ struct Gru { SConv z, r, q; };
 void conv_gru(Exec& e, const Gru& g, const float* h, int ld_h, const float* x, int ld_x, int c, int u, PointCloud& pc1,
               PointCloud& pc2, const Globals& G, const int32_t* idx1, const float* w1, const int32_t* idx1_hash, float* out,
               int ld_out) {
-  Mat hx{alloc<float>(e, (size_t)u * 2 * c), 2 * c};
+  Mat hx{alloc<float>(e, (size_t)u * 2 * c), 2 * c, nullptr};
   copy_cols(e, h, ld_h, u, c, hx.p, hx.ld);
   copy_cols(e, x, ld_x, u, c, hx.p + c, hx.ld);
   Mat z_pre = sconv3d(e, g.z, hx.p, hx.ld, u, pc1, G, idx1, w1);
   Mat r_pre = sconv3d(e, g.r, hx.p, hx.ld, u, pc2, G, idx1_hash, w1);   // the reference's stale-cache quirk
-  Mat rhx{alloc<float>(e, (size_t)u * 2 * c), 2 * c};
+  Mat rhx{alloc<float>(e, (size_t)u * 2 * c), 2 * c, nullptr};
   RUN(e, 1, ep_gru_rh(r_pre.p, r_pre.ld, h, ld_h, x, ld_x, u, c, rhx.p, rhx.ld, e.st));
   Mat q_pre = sconv3d(e, g.q, rhx.p, rhx.ld, u, pc1, G, idx1, w1);
   RUN(e, 1, ep_gru_out(z_pre.p, z_pre.ld, q_pre.p, q_pre.ld, h, ld_h, u, c, out, ld_out, e.st));
@@ -604,40 +625,43 @@ int ep_exec_spvcnn(const int64_t* desc, const int64_t* globals, const float* pts
   PointCloud pc;
   build_pc(e, pc, pts, n, vres, true);                                             // initial_voxelize
   VoxelSet& v0 = pc.vox;
-  Mat x0 = voxelize(e, pc.csr1, feat, ld_feat, cin0);
-  x0 = conv_bn_relu(e, x0.p, x0.ld, v0.m, kmap_k3(e, v0, G), stem, stem_bn, v0.m);       // stem
+  const bool hl = stem.w_hl != nullptr;    // half-pair mode: producers write the operand copy their tensor-core consumer gathers
+  Mat x0 = voxelize(e, pc.csr1, feat, ld_feat, cin0, hl);
+  x0 = conv_bn_relu(e, x0, v0.m, kmap_k3(e, v0, G), stem, stem_bn, v0.m);                  // stem
   const int32_t* idx1; const float* w1;
   taps(e, pc, v0, idx1, w1);
   Mat z0 = devoxelize(e, x0, cs[0], idx1, w1, n, nullptr, 0);                      // voxel_to_point(x0, z)
-  Mat x1 = voxelize(e, pc.csr1, z0.p, z0.ld, cs[0]);                               // point_to_voxel(x0, z0)
+  Mat x1 = voxelize(e, pc.csr1, z0.p, z0.ld, cs[0], hl);                           // point_to_voxel(x0, z0)
   VoxelSet v1, v2;
   int32_t *down01, *up10, *down12, *up21;
   downsample(e, v0, G, v1, down01, up10);
-  x1 = conv_bn_relu(e, x1.p, x1.ld, v0.m, down01, down1, down1_bn, v1.m);
-  x1 = residual_block(e, x1, kmap_k3(e, v1, G), s1a, v1.m);
-  x1 = residual_block(e, x1, kmap_k3(e, v1, G), s1b, v1.m);
+  x1 = conv_bn_relu(e, x1, v0.m, down01, down1, down1_bn, v1.m, nullptr, 0, hl);
+  x1 = residual_block(e, x1, kmap_k3(e, v1, G), s1a, v1.m, true);
+  x1 = residual_block(e, x1, kmap_k3(e, v1, G), s1b, v1.m, true);
   downsample(e, v1, G, v2, down12, up21);
-  Mat x2 = conv_bn_relu(e, x1.p, x1.ld, v1.m, down12, down2, down2_bn, v2.m);
-  x2 = residual_block(e, x2, kmap_k3(e, v2, G), s2a, v2.m);
-  x2 = residual_block(e, x2, kmap_k3(e, v2, G), s2b, v2.m);
+  Mat x2 = conv_bn_relu(e, x1, v1.m, down12, down2, down2_bn, v2.m, nullptr, 0, hl);
+  x2 = residual_block(e, x2, kmap_k3(e, v2, G), s2a, v2.m, true);
+  x2 = residual_block(e, x2, kmap_k3(e, v2, G), s2b, v2.m, false);
   const int32_t* idx4; const float* w4;
   taps(e, pc, v2, idx4, w4);
-  Mat p0 = conv_bn_relu(e, z0.p, z0.ld, n, nullptr, pt0, pt0_bn, n);                  // point_transforms[0](z0.F)
+  Mat z0m{z0.p, z0.ld, nullptr};
+  Mat p0 = conv_bn_relu(e, z0m, n, nullptr, pt0, pt0_bn, n);                       // point_transforms[0](z0.F)
   Mat z1 = devoxelize(e, x2, cs[2], idx4, w4, n, p0.p, p0.ld);
   const Csr csr2 = csr_for(e, pc, v2);
-  Mat y3 = voxelize(e, csr2, z1.p, z1.ld, cs[2]);                                  // point_to_voxel(x2, z1)
+  Mat y3 = voxelize(e, csr2, z1.p, z1.ld, cs[2], hl);                              // point_to_voxel(x2, z1)
   // up1: transposed conv to stride 2, concat skip x1, two residual blocks
-  Mat cat1{alloc<float>(e, (size_t)v1.m * (cs[3] + cs[1])), cs[3] + cs[1]};
-  conv_bn_relu(e, y3.p, y3.ld, v2.m, up21, dec1, dec1_bn, v1.m, cat1.p, cat1.ld);
+  Mat cat1{alloc<float>(e, (size_t)v1.m * (cs[3] + cs[1])), cs[3] + cs[1], nullptr};
+  conv_bn_relu(e, y3, v2.m, up21, dec1, dec1_bn, v1.m, cat1.p, cat1.ld);
   copy_cols(e, x1.p, x1.ld, v1.m, cs[1], cat1.p + cs[3], cat1.ld);
-  y3 = residual_block(e, cat1, kmap_k3(e, v1, G), u1a, v1.m);
-  y3 = residual_block(e, y3, kmap_k3(e, v1, G), u1b, v1.m);
-  Mat cat0{alloc<float>(e, (size_t)v0.m * (cs[4] + cs[0])), cs[4] + cs[0]};
-  conv_bn_relu(e, y3.p, y3.ld, v1.m, up10, dec2, dec2_bn, v0.m, cat0.p, cat0.ld);
+  y3 = residual_block(e, cat1, kmap_k3(e, v1, G), u1a, v1.m, true);
+  y3 = residual_block(e, y3, kmap_k3(e, v1, G), u1b, v1.m, true);
+  Mat cat0{alloc<float>(e, (size_t)v0.m * (cs[4] + cs[0])), cs[4] + cs[0], nullptr};
+  conv_bn_relu(e, y3, v1.m, up10, dec2, dec2_bn, v0.m, cat0.p, cat0.ld);
   copy_cols(e, x0.p, x0.ld, v0.m, cs[0], cat0.p + cs[4], cat0.ld);
-  Mat y4 = residual_block(e, cat0, kmap_k3(e, v0, G), u2a, v0.m);
-  y4 = residual_block(e, y4, kmap_k3(e, v0, G), u2b, v0.m);
-  Mat p1 = conv_bn_relu(e, z1.p, z1.ld, n, nullptr, pt1, pt1_bn, n);                  // point_transforms[1](z1.F)
+  Mat y4 = residual_block(e, cat0, kmap_k3(e, v0, G), u2a, v0.m, true);
+  y4 = residual_block(e, y4, kmap_k3(e, v0, G), u2b, v0.m, false);
+  Mat z1m{z1.p, z1.ld, nullptr};
+  Mat p1 = conv_bn_relu(e, z1m, n, nullptr, pt1, pt1_bn, n);                       // point_transforms[1](z1.F)
   devoxelize(e, y4, cs[4], idx1, w1, n, p1.p, p1.ld, out, ld_out);
   return finish(e, stats);
 }
@@ -735,19 +759,19 @@ int ep_exec_init_head(const int64_t* desc, const int64_t* globals, const float* 
   RUN(e, 1, ep_kmap_build(coords, m, 1, G.subm3, 27, t.keys, t.vals, t.cap, sx, sy, sz, k3, e.st));
   auto nbr_of = [&](const Conv& c) -> const int32_t* { return c.K == 1 ? nullptr : k3; };
 
-  Mat x{alloc<float>(e, (size_t)m * d), d};
+  Mat x{alloc<float>(e, (size_t)m * d), d, nullptr};
   float* part0 = alloc<float>(e, (size_t)ep_spconv_num_row_tiles(m) * 2 * d);
   RUN(e, 1, ep_colstats(var, ld_var, m, d, part0, e.st));
   const float* ss0 = bn_ss(e, part0, m, norm0);
   RUN(e, 1, ep_affine_act(var, ld_var, ss0, nullptr, 0, nullptr, 0, m, d, x.p, x.ld, e.st));
 
   // ELAN: cat = [f1 | f2 | c3 | c4 | c5 | c6]
-  Mat cat{alloc<float>(e, (size_t)m * 4 * d), 4 * d};
+  Mat cat{alloc<float>(e, (size_t)m * 4 * d), 4 * d, nullptr};
   auto block = [&](int i, const float* in, int ld_in, float* out, int ld_o) {
     Mat y = spconv(e, in, ld_in, m, ec[i], nbr_of(ec[i]), m, nullptr);
     if (!out) { out = y.p; ld_o = y.ld; }
     layernorm(e, y.p, y.ld, nullptr, 0, 0, en[i], 1, m, out, ld_o);
-    return Mat{out, ld_o};
+    return Mat{out, ld_o, nullptr};
   };
   block(0, x.p, x.ld, cat.p, cat.ld);
   block(1, x.p, x.ld, cat.p + d, cat.ld);

@@ -37,7 +37,7 @@ constexpr int MAX_STAGES = 8;
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                   // leading byte offset: unused for swizzled K-major operands
+                                            // leading byte offset 0: one swizzle atom along K (unused for swizzled K-major)
   d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset: one 8-row x 128-byte swizzle atom
   d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
@@ -320,6 +320,105 @@ hl_split_kernel(const float* __restrict__ src, int ld, int c, long long m, int n
   d[4 + oct] = *reinterpret_cast<const uint4*>(l);
 }
 
+__device__ __forceinline__ void hl_store8(uint4* __restrict__ dst_slab_row /* 8 x uint4 */, int oct, const float (&v)[8],
+                                          int* __restrict__ overflow) {
+  __half h[8], l[8];
+  bool big = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __float2half_rn(v[i]);
+    l[i] = __float2half_rn((v[i] - __half2float(h[i])) * 2048.f);
+    big |= fabsf(v[i]) > 65000.f;
+  }
+  if (big && overflow) atomicOr(overflow, 1);
+  dst_slab_row[oct] = *reinterpret_cast<const uint4*>(h);
+  dst_slab_row[4 + oct] = *reinterpret_cast<const uint4*>(l);
+}
+
+// BatchNorm apply (+ residual, + ReLU) that ALSO writes the half-pair copy the next sparse conv gathers (fuses
+// ep_affine_act with ep_hl_split_rows):  y = act(a*sa + ta [+ b*sb + tb]);  out (fp32, may alias a) and out_hl.
+__global__ void __launch_bounds__(256)
+hl_affine_act_kernel(const float* __restrict__ a, int ld_a, const float* __restrict__ ssa, const float* __restrict__ b, int ld_b,
+                     const float* __restrict__ ssb, int relu, long long m, int c, int nslab, float* __restrict__ out, int ld_out,
+                     uint4* __restrict__ out_hl, int* __restrict__ overflow) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m * nslab * 4) return;
+  const int oct = (int)(t & 3);
+  const long long rs = t >> 2;
+  const int slab = (int)(rs % nslab);
+  const long long row = rs / nslab;
+  const int ch0 = slab * 32 + oct * 8;
+  float v[8];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int ch = ch0 + 4 * g;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ch < c) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(a + row * ld_a + ch));
+      x[0] = f.x; x[1] = f.y; x[2] = f.z; x[3] = f.w;
+      float y[4] = {0.f, 0.f, 0.f, 0.f};
+      if (b) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(b + row * ld_b + ch));
+        y[0] = q.x; y[1] = q.y; y[2] = q.z; y[3] = q.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = ch + j;
+        float r = 0.f;
+        if (col < c) {
+          r = x[j];
+          if (ssa) r = fmaf(r, ssa[col], ssa[c + col]);
+          if (b) {
+            float w = y[j];
+            if (ssb) w = fmaf(w, ssb[col], ssb[c + col]);
+            r += w;
+          }
+          if (relu) r = fmaxf(r, 0.f);
+        }
+        x[j] = r;
+      }
+      *reinterpret_cast<float4*>(out + row * ld_out + ch) = make_float4(x[0], x[1], x[2], x[3]);
+    }
+    v[4 * g + 0] = x[0]; v[4 * g + 1] = x[1]; v[4 * g + 2] = x[2]; v[4 * g + 3] = x[3];
+  }
+  hl_store8(out_hl + (row * nslab + slab) * 8, oct, v, overflow);
+}
+
+// voxelisation (segmented mean of point rows, as ep_segment_mean) that also writes the half-pair copy of its output
+__global__ void __launch_bounds__(256)
+hl_segment_mean_kernel(const float* __restrict__ feat, int ld_in, int c, const int* __restrict__ perm,
+                       const int* __restrict__ seg_start, const int* __restrict__ seg_end, long long m, int nslab,
+                       float* __restrict__ out, int ld_out, uint4* __restrict__ out_hl, int* __restrict__ overflow) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m * nslab * 4) return;
+  const int oct = (int)(t & 3);
+  const long long rs = t >> 2;
+  const int slab = (int)(rs % nslab);
+  const long long s = rs / nslab;
+  const int ch0 = slab * 32 + oct * 8;
+  const int a = seg_start[s], b = seg_end[s];
+  const float cnt = (float)(b - a);
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool g0 = ch0 < c, g1 = ch0 + 4 < c;      // whole quads: the input's padding columns (ld % 4 == 0) are carried along
+  if (g0) {
+    for (int p = a; p < b; ++p) {
+      const float* src = feat + (size_t)perm[p] * ld_in + ch0;
+      const float4 x = *reinterpret_cast<const float4*>(src);
+      v[0] += __fdiv_rn(x.x, cnt); v[1] += __fdiv_rn(x.y, cnt); v[2] += __fdiv_rn(x.z, cnt); v[3] += __fdiv_rn(x.w, cnt);
+      if (g1) {
+        const float4 y = *reinterpret_cast<const float4*>(src + 4);
+        v[4] += __fdiv_rn(y.x, cnt); v[5] += __fdiv_rn(y.y, cnt); v[6] += __fdiv_rn(y.z, cnt); v[7] += __fdiv_rn(y.w, cnt);
+      }
+    }
+    *reinterpret_cast<float4*>(out + (size_t)s * ld_out + ch0) = make_float4(v[0], v[1], v[2], v[3]);
+    if (g1) *reinterpret_cast<float4*>(out + (size_t)s * ld_out + ch0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (ch0 + j >= c) v[j] = 0.f;               // the half-pair copy is zero beyond the valid channels
+  hl_store8(out_hl + (s * nslab + slab) * 8, oct, v, overflow);
+}
+
 // debugging aid: one warp gathers 128 rows of slab `slab` with 32 gather4 and dumps the raw 16 KB of shared memory
 __global__ void __launch_bounds__(32)
 hl_probe_gather4_kernel(const __grid_constant__ CUtensorMap tm_a, const int* __restrict__ rows128, int slab,
@@ -383,6 +482,8 @@ bool make_map(CUtensorMap* map, const void* base, uint64_t row_halfs, uint64_t r
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int g_hl_debug = 0;   // last failure site of ep_spconv_hl_fwd (1 map A, 2 map B, 3 smem attribute, 4 launch); ep_hl_debug_code()
+
 inline int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -417,6 +518,32 @@ int ep_hl_split_rows(const float* src, int ld_src, int c, int64_t m, uint16_t* d
   return EP_OK;
 }
 
+// ep_affine_act + half-pair copy of the result for the next sparse conv (out may alias a; out_hl [m][ep_hl_slabs(c)][64])
+int ep_hl_affine_act(const float* a, int ld_a, const float* ss_a, const float* b, int ld_b, const float* ss_b, int relu, int64_t m,
+                     int c, float* out, int ld_out, uint16_t* out_hl, int32_t* overflow, cudaStream_t stream) {
+  if (m <= 0 || c < 1 || ld_a % 4 || ld_out % 4 || (b && ld_b % 4) || !out_hl) return EP_ERR_ARG;
+  if (((uintptr_t)a & 15) || ((uintptr_t)out & 15) || ((uintptr_t)out_hl & 15) || (b && ((uintptr_t)b & 15))) return EP_ERR_ARG;
+  const int nslab = (c + 31) / 32;
+  const long long total = (long long)m * nslab * 4;
+  hl_affine_act_kernel<<<ep_div_up(total, 256), 256, 0, stream>>>(a, ld_a, ss_a, b, ld_b, ss_b, relu, (long long)m, c, nslab, out, ld_out,
+                                                                  reinterpret_cast<uint4*>(out_hl), overflow);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
+// ep_segment_mean + half-pair copy of the result
+int ep_hl_segment_mean(const float* feat, int ld_in, int c, const int32_t* perm, const int32_t* seg_start, const int32_t* seg_end,
+                       int64_t m, float* out, int ld_out, uint16_t* out_hl, int32_t* overflow, cudaStream_t stream) {
+  if (m <= 0 || c < 1 || ld_in % 4 || ld_out % 4 || !out_hl) return EP_ERR_ARG;
+  if (((uintptr_t)feat & 15) || ((uintptr_t)out & 15) || ((uintptr_t)out_hl & 15)) return EP_ERR_ARG;
+  const int nslab = (c + 31) / 32;
+  const long long total = (long long)m * nslab * 4;
+  hl_segment_mean_kernel<<<ep_div_up(total, 256), 256, 0, stream>>>(feat, ld_in, c, perm, seg_start, seg_end, (long long)m, nslab, out,
+                                                                    ld_out, reinterpret_cast<uint4*>(out_hl), overflow);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
 size_t ep_spconv_hl_workspace_bytes(int64_t m_out, int npad, int K) {
   const int s = hl_splits(m_out, npad, K);
   return s > 1 ? (size_t)s * (size_t)m_out * (size_t)npad * sizeof(float) : 0;
@@ -443,18 +570,19 @@ int ep_spconv_hl_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t
   const int tmem_cols = pow2_cols(4 * nt);
   if (tmem_cols > 512) return EP_ERR_UNSUPPORTED;
   CUtensorMap tm_a, tm_b;
-  if (!make_map(&tm_a, in_hl, (uint64_t)nslab * 64, (uint64_t)m_in, 1)) return EP_ERR_CUDA;
-  if (!make_map(&tm_b, w_hl, 64, (uint64_t)K * nslab * npad, (uint32_t)nt)) return EP_ERR_CUDA;
+  if (!make_map(&tm_a, in_hl, (uint64_t)nslab * 64, (uint64_t)m_in, 1)) { g_hl_debug = 1; return EP_ERR_CUDA; }
+  if (!make_map(&tm_b, w_hl, 64, (uint64_t)K * nslab * npad, (uint32_t)nt)) { g_hl_debug = 2; return EP_ERR_CUDA; }
   const int stage_bytes = A_STAGE + nt * 128;
   // TMEM decides how many CTAs share an SM (512 columns): give each the deepest ring its share of shared memory allows
   const int ctas_per_sm = 512 / tmem_cols >= 2 ? 2 : 1;
-  const int budget = (ctas_per_sm == 2 ? 110 : 220) * 1024 - K * NBS * 4 - 1024;
+  // shared memory per SM: 228 KB, per CTA at most 227 KB incl. ~4.4 KB of static barriers / reduction scratch + 1 KB reserved
+  const int budget = (ctas_per_sm == 2 ? 104 : 216) * 1024 - K * NBS * 4 - 1024;
   int nstage = budget / stage_bytes;
   if (nstage > MAX_STAGES) nstage = MAX_STAGES;
   if (nstage < 2) return EP_ERR_UNSUPPORTED;
   const size_t smem = (size_t)nstage * stage_bytes + (size_t)K * NBS * sizeof(int) + 1024;
-  static const cudaError_t attr = cudaFuncSetAttribute(spconv_hl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-  if (attr != cudaSuccess) return EP_ERR_CUDA;
+  static const cudaError_t attr = cudaFuncSetAttribute(spconv_hl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+  if (attr != cudaSuccess) { g_hl_debug = 3; return EP_ERR_CUDA; }
   const int splits = hl_splits(m_out, npad, K);
   if (splits > 1 && workspace_bytes < ep_spconv_hl_workspace_bytes(m_out, npad, K)) return EP_ERR_WORKSPACE;
   float* partial = splits > 1 ? (float*)workspace : nullptr;
@@ -467,9 +595,11 @@ int ep_spconv_hl_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t
     const int s = ep_internal_splitk_reduce(partial, splits, (int)m_out, npad, cout, bias, out, ld_out, bn_partial, stream);
     if (s != EP_OK) return s;
   }
-  EP_CHECK_LAUNCH();
+  if (cudaGetLastError() != cudaSuccess) { g_hl_debug = 4; return EP_ERR_CUDA; }
   return EP_OK;
 }
+
+int ep_hl_debug_code(void) { return g_hl_debug; }
 
 // Debug entry: gathers the 128 rows `rows128` (device int32[128]; any value, out-of-range rows must read as zeros) of slab
 // `slab` of in_hl [m_in][nslab][64] with 32 gather4 and returns the raw shared-memory image (16 KB) + status (1 ok, -1 timeout).

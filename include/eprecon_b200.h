@@ -122,10 +122,15 @@ int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, in
  * w_hl [K][nslab][npad][64] halfs; npad = cout rounded up to 16 (to 128 when larger). */
 int ep_hl_slabs(int c);
 int ep_hl_split_rows(const float* src, int ld_src, int c, int64_t m, uint16_t* dst, int32_t* overflow, cudaStream_t stream);
+int ep_hl_affine_act(const float* a, int ld_a, const float* ss_a, const float* b, int ld_b, const float* ss_b, int relu, int64_t m,
+                     int c, float* out, int ld_out, uint16_t* out_hl, int32_t* overflow, cudaStream_t stream);
+int ep_hl_segment_mean(const float* feat, int ld_in, int c, const int32_t* perm, const int32_t* seg_start, const int32_t* seg_end,
+                       int64_t m, float* out, int ld_out, uint16_t* out_hl, int32_t* overflow, cudaStream_t stream);
 size_t ep_spconv_hl_workspace_bytes(int64_t m_out, int npad, int K);
 int ep_spconv_hl_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t* nbr, int K, const uint16_t* w_hl, int npad,
                      int cout, const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, void* workspace,
                      size_t workspace_bytes, int neg_row_mode, cudaStream_t stream);
+int ep_hl_debug_code(void);   /* last failure site of ep_spconv_hl_fwd: 1 map A, 2 map B, 3 smem attribute, 4 launch */
 int ep_hl_probe_gather4(const uint16_t* in_hl, int64_t m_in, int nslab, const int32_t* rows128, int slab, void* out16k,
                         int32_t* status, cudaStream_t stream);
 int ep_colstats(const float* x, int ld, int64_t m, int c, float* bn_partial, cudaStream_t stream);

@@ -95,7 +95,7 @@ def probe_conv(neg_mode):
             err = rel(y[:, :cout].cpu(), want)
             s_ok = bool(torch.allclose(part.cpu()[:, 0].sum(0), y[:, :cout].cpu().sum(0), rtol=1e-4, atol=1e-3))
         except Exception as e:  # noqa: BLE001
-            err, s_ok = repr(e), False
+            err, s_ok = repr(e)[:200] + f" debug_code={_lib.lib().ep_hl_debug_code()}", False
         res.append({"shape": (m_in, m_out, cin, cout, K), "rel_err": err, "bn_partial_ok": s_ok})
         print("conv", neg_mode, res[-1], flush=True)
     OUT[f"conv_neg{neg_mode}"] = res
