@@ -110,16 +110,35 @@ struct Exec {
   char* base;
   size_t cap, off, peak;
   int32_t* pinned;
+  int32_t* counters;
   int err;
   size_t launches;
 };
 
 thread_local int32_t* tl_pinned = nullptr;
 
+// zeroed ticket counters for the fused split-K reduction / BatchNorm finalisation of csrc/spconv_hl.cu: one buffer per
+// (host thread, stream); the kernels leave it zeroed, so it is cleared exactly once
+constexpr int kCounters = 1024;
+struct CounterSlot { cudaStream_t st; int32_t* p; };
+thread_local std::vector<CounterSlot>* tl_counters = nullptr;
+
+int32_t* counters_for(cudaStream_t st) {
+  if (!tl_counters) tl_counters = new std::vector<CounterSlot>();
+  for (auto& c : *tl_counters)
+    if (c.st == st) return c.p;
+  int32_t* p = nullptr;
+  if (cudaMalloc((void**)&p, kCounters * sizeof(int32_t)) != cudaSuccess) return nullptr;
+  if (cudaMemsetAsync(p, 0, kCounters * sizeof(int32_t), st) != cudaSuccess) { cudaFree(p); return nullptr; }
+  tl_counters->push_back({st, p});
+  return p;
+}
+
 inline bool exec_init(Exec& e, void* arena, size_t arena_bytes, cudaStream_t st) {
   e.st = st; e.base = (char*)arena; e.cap = arena_bytes; e.off = 0; e.peak = 0; e.err = EP_OK; e.launches = 0;
   if (!tl_pinned && cudaHostAlloc((void**)&tl_pinned, 256, cudaHostAllocDefault) != cudaSuccess) { tl_pinned = nullptr; return false; }
   e.pinned = tl_pinned;
+  e.counters = counters_for(st);
   return arena != nullptr && ((uintptr_t)arena & 255) == 0;
 }
 
@@ -290,11 +309,15 @@ Mat devoxelize(Exec& e, const Mat& v, int c, const int32_t* idx, const float* w,
   return o;
 }
 
+float* bn_ss(Exec& e, const float* part, int m, const Norm& bn);
+
 // out[j,:cout] = bias + sum_k W[k]^T x[nbr[j,k]]; K == 1 runs on the fp32 FFMA kernel, K > 1 on the tensor cores: the TMA
 // gather kernel on half-pair operands (csrc/spconv_hl.cu; the input's m_in rows are split right here) when the descriptor
 // carries w_hl, else the round-1 3xTF32 kernel
+// bn + ss: also produce the train-mode BatchNorm scale / shift of the output (fused into the conv kernel where it pays)
 Mat spconv(Exec& e, const float* x, int ldx, int m_in, const Conv& cv, const int32_t* nbr, int m_out, float** part,
-           float* out = nullptr, int ld_out = 0, const uint16_t* x_hl = nullptr) {
+           float* out = nullptr, int ld_out = 0, const uint16_t* x_hl = nullptr, const Norm* bn = nullptr,
+           const float** ss = nullptr) {
   const int c4 = ceil4(cv.cout);
   Mat o{out, ld_out, nullptr};
   if (!out) {
@@ -321,6 +344,7 @@ Mat spconv(Exec& e, const float* x, int ldx, int m_in, const Conv& cv, const int
   if (cv.K == 1) {
     RUN(e, 1, ep_spconv_fwd(x, ldx, cv.cin, nbr, 1, cv.w, c4, cv.cout, cv.bias, o.p, o.ld, m_out, pp, e.st));
   } else if (cv.w_hl) {
+    float* ssp = bn ? alloc<float>(e, 2 * (size_t)bn->c) : nullptr;
     const size_t mark = e.off;
     const uint16_t* xs = x_hl;
     if (!xs) {      // no producer wrote the half-pair copy (concat buffers, column slices): split here
@@ -330,9 +354,13 @@ Mat spconv(Exec& e, const float* x, int ldx, int m_in, const Conv& cv, const int
     }
     const size_t wsb = ep_spconv_hl_workspace_bytes(m_out, cv.npad, cv.K);
     void* ws = wsb ? (void*)alloc<char>(e, wsb) : nullptr;
-    RUN(e, wsb ? 2 : 1, ep_spconv_hl_fwd(xs, m_in, cv.cin, nbr, cv.K, cv.w_hl, cv.npad, cv.cout, cv.bias, o.p, o.ld, m_out, pp, ws,
-                                        wsb, 0, e.st));
+    RUN(e, ep_spconv_hl_launches(m_out, cv.npad, cv.K, e.counters != nullptr, bn != nullptr),
+        ep_spconv_hl_fused_fwd(xs, m_in, cv.cin, nbr, cv.K, cv.w_hl, cv.npad, cv.cout, cv.bias, o.p, o.ld, m_out, pp, ws, wsb, 0,
+                               e.counters, kCounters, bn ? bn->gamma : nullptr, bn ? bn->beta : nullptr, bn ? bn->eps : 0.f, ssp,
+                               e.st));
     if (!e.err) e.off = mark;
+    if (bn) *ss = ssp;
+    return o;
   } else {
     const size_t mark = e.off;
     const size_t wsb = ep_spconv_tc_workspace_bytes(m_out, cv.npad, cv.K);
@@ -341,6 +369,7 @@ Mat spconv(Exec& e, const float* x, int ldx, int m_in, const Conv& cv, const int
                                ws, wsb, e.st));
     if (!e.err) e.off = mark;
   }
+  if (bn) *ss = bn_ss(e, pp, m_out, *bn);
   return o;
 }
 
@@ -364,8 +393,8 @@ void bn_apply(Exec& e, Mat& y, const float* ss, const float* b, int ld_b, const 
 Mat conv_bn_relu(Exec& e, const Mat& x, int m_in, const int32_t* nbr, const Conv& cv, const Norm& bn, int m_out,
                  float* out = nullptr, int ld_out = 0, bool want_hl = false) {
   float* part = nullptr;
-  Mat y = spconv(e, x.p, x.ld, m_in, cv, nbr, m_out, &part, out, ld_out, x.hl);
-  const float* ss = bn_ss(e, part, m_out, bn);
+  const float* ss = nullptr;
+  Mat y = spconv(e, x.p, x.ld, m_in, cv, nbr, m_out, &part, out, ld_out, x.hl, &bn, &ss);
   bn_apply(e, y, ss, nullptr, 0, nullptr, m_out, cv.cout, want_hl);
   return y;
 }
@@ -384,14 +413,14 @@ Mat residual_block(Exec& e, const Mat& x, const int32_t* nbr, const ResBlock& b,
   const bool hl = b.c2.w_hl != nullptr;
   Mat t = conv_bn_relu(e, x, m, nbr, b.c1, b.b1, m, nullptr, 0, hl);
   float* part_u = nullptr;
-  Mat u = spconv(e, t.p, t.ld, m, b.c2, nbr, m, &part_u, nullptr, 0, t.hl);
-  const float* ss_u = bn_ss(e, part_u, m, b.b2);
+  const float* ss_u = nullptr;
+  Mat u = spconv(e, t.p, t.ld, m, b.c2, nbr, m, &part_u, nullptr, 0, t.hl, &b.b2, &ss_u);
   if (!b.has_down) {
     bn_apply(e, u, ss_u, x.p, x.ld, nullptr, m, b.c2.cout, want_hl && hl);
   } else {
     float* part_d = nullptr;
-    Mat d = spconv(e, x.p, x.ld, m, b.cd, nullptr, m, &part_d);
-    const float* ss_d = bn_ss(e, part_d, m, b.bd);
+    const float* ss_d = nullptr;
+    Mat d = spconv(e, x.p, x.ld, m, b.cd, nullptr, m, &part_d, nullptr, 0, nullptr, &b.bd, &ss_d);
     bn_apply(e, u, ss_u, d.p, d.ld, ss_d, m, b.c2.cout, want_hl && hl);
   }
   return u;

@@ -24,6 +24,9 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+extern "C" int ep_bn_finalize(const float* bn_partial, int num_row_tiles, int c, int64_t m, float eps, const float* gamma,
+                              const float* beta, float* scale_shift, float* mean_var, cudaStream_t stream);
+
 namespace {
 
 using namespace eptc;
@@ -320,6 +323,339 @@ hl_split_kernel(const float* __restrict__ src, int ld, int c, long long m, int n
   d[4 + oct] = *reinterpret_cast<const uint4*>(l);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// cp.async producers.  Measured on B200 (profiles/r02_probe_hl_v1_tma_gather4_timing.json): the TMA unit retires a
+// tile::gather4 of 128-byte rows in ~62 cycles (1.8-2.3 TB/s chip-wide, 8 bytes / clock / SM), slower than the register
+// producers it replaced.  The half-pair layout makes the cheaper alternative possible: a 16-byte cp.async (LDGSTS) lands a
+// gathered chunk directly in its swizzled slot of the UMMA operand -- no register staging, no conversion, no STS -- 8
+// lanes per 128-byte row, so a warp instruction moves 4 whole rows (4 L1TEX wavefronts for 512 bytes).
+constexpr int CP_THREADS = 256;            // warps 0-3: cp.async producers, warp 4 lane 0: MMA issuer, all 8 warps: epilogue
+constexpr int CP_PRODUCERS = 128;
+constexpr int CP_LAG_MIN = 2;              // a thread keeps the loads of LAG + 1 stages in flight (template parameter)
+
+template <bool CA>
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  if (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  else asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// CA: gathered chunks allocate in L1 (a tile re-gathers each of its ~370 distinct rows ~9 times over the 27 offsets) or bypass
+// it; CP_LAG: ring depth in flight per thread.
+template <bool CA, int CP_LAG>
+__global__ void __launch_bounds__(CP_THREADS)
+spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ CUtensorMap tm_b,
+                    const int* __restrict__ nbr, int K, int nslab, int npad, int nt, int tmem_cols, int nstage, int cout,
+                    const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m_out,
+                    float* __restrict__ bn_partial, int bn_rows, int splits, float* __restrict__ partial,
+                    int* __restrict__ counters /* zeroed tickets: [0] finished tiles, [1 + tile] finished splits; or null */,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float bn_eps, float* __restrict__ ss_out) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int b_stage = nt * 128;
+  const int stage_bytes = A_STAGE + b_stage;
+  int* s_nbr = reinterpret_cast<int*>(smem + (size_t)nstage * stage_bytes);       // [K][NBS]
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
+  __shared__ uint64_t all_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_mask, s_used;
+  __shared__ float s_red[8][128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * HTM;
+  const int col0 = blockIdx.y * nt;
+  const int kb = (int)(((long long)blockIdx.z * K) / splits), ke = (int)(((long long)(blockIdx.z + 1) * K) / splits);
+
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    // full: every producer thread arrives once per stage + the expect_tx arrive that covers the weight tile's TMA bytes
+    for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], CP_PRODUCERS + 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&all_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_mask = 0;
+    s_used = 0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    constexpr int PU = 4;
+    const int total = HTM * K;
+    const long long base = (long long)row0 * K, lim = (long long)m_out * K;
+    unsigned mine = 0;
+    for (int e0 = 0; e0 < total; e0 += CP_THREADS * PU) {
+      int v[PU];
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int e = e0 + u * CP_THREADS + tid;
+        v[u] = -1;
+        if (e < total && base + e < lim) v[u] = nbr ? __ldg(nbr + base + e) : row0 + e;
+      }
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int e = e0 + u * CP_THREADS + tid;
+        if (e < total) {
+          const int r = e / K, kq = e - r * K;
+          s_nbr[kq * NBS + r] = v[u];
+          if (v[u] >= 0 && kq >= kb && kq < ke) mine |= 1u << kq;
+        }
+      }
+    }
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if (lane == 0 && mine) atomicOr(&s_mask, (int)mine);
+  }
+  __syncthreads();
+  const unsigned kmask = (unsigned)s_mask;
+  const uint32_t tmem_d = tmem_base_s;
+  const int T = __popc(kmask) * nslab;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------- producers: thread = chunk (tid & 7) of rows (tid >> 3) + 16 i
+    const int chunk = tid & 7, rbase = tid >> 3;
+    const uint32_t dst_thread = (uint32_t)(rbase * 128 + ((chunk ^ (rbase & 7)) << 4));   // SWIZZLE_128B: chunk ^ (row % 8)
+    const size_t pitch = (size_t)nslab * 128;
+    const uint8_t* src_thread = in_hl + chunk * 16;
+    unsigned rem = kmask;
+    int k = 0, c = 0;
+    const uint8_t* rowp[8];
+    auto set_k = [&]() {
+      k = __ffs(rem) - 1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = s_nbr[k * NBS + rbase + 16 * i];
+        rowp[i] = r >= 0 ? src_thread + (size_t)r * pitch : nullptr;
+      }
+    };
+    if (T > 0) set_k();
+    int stage = 0, round = 0;          // issue cursor
+    int rstage = 0;                    // retire cursor
+    for (int t = 0; t < T + CP_LAG; ++t) {
+      if (t < T) {
+        if (round > 0) mbar_wait_b(&empty_bar[stage], (round - 1) & 1);
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        if (tid == 0) {
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_stage);
+          tma_tile2d(&tm_b, &full_bar[stage], smem + (size_t)stage * stage_bytes + A_STAGE, 0, (k * nslab + c) * npad + col0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint8_t* p = rowp[i];
+          cp_async16<CA>(sa + dst_thread + i * (16 * 128), p ? p + c * 128 : in_hl, p ? 16u : 0u);   // missing neighbour: zero fill
+        }
+        if (++c == nslab) {
+          c = 0;
+          rem &= rem - 1;
+          if (rem) set_k();
+        }
+        if (++stage == nstage) { stage = 0; ++round; }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");          // (empty groups past the end keep the wait depth uniform)
+      if (t >= CP_LAG) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(CP_LAG) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+        mbar_arrive(&full_bar[rstage]);
+        if (++rstage == nstage) rstage = 0;
+      }
+    }
+  } else if (warp == 4 && lane == 0) {
+    // ------------------------------------------------------------- MMA issuer (one thread)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(HTM >> 4) << 24);   // f16 x f16 -> f32
+    uint32_t used = 0;
+    int stage = 0, round = 0;
+    for (int t = 0; t < T; ++t) {
+      mbar_wait_b(&full_bar[stage], round & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + A_STAGE;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const uint64_t dah = umma_desc_sw128(sa + kk * 32), dal = umma_desc_sw128(sa + 64 + kk * 32);
+        const uint64_t dbh = umma_desc_sw128(sb + kk * 32), dbl = umma_desc_sw128(sb + 64 + kk * 32);
+        const int am = (t * 2 + kk) % 3;
+        umma_f16(tmem_d + am * nt, dah, dbh, idesc, (used >> am) & 1u);
+        used |= 1u << am;
+        umma_f16(tmem_d + 3 * nt, dal, dbh, idesc, (used >> 3) & 1u);
+        used |= 1u << 3;
+        umma_f16(tmem_d + 3 * nt, dah, dbl, idesc, 1u);
+      }
+      umma_commit(&empty_bar[stage]);
+      if (++stage == nstage) { stage = 0; ++round; }
+    }
+    umma_commit(&all_done);
+    s_used = (int)used;
+  }
+  __syncthreads();
+  // ------------------------------------------------------------- epilogue: warp w owns TMEM lanes 32 (w & 3) and one half of the columns
+  if (T > 0) mbar_wait_b(&all_done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t used = (uint32_t)s_used;
+  const int q = warp & 3, half = warp >> 2;
+  const int row = row0 + q * 32 + lane;
+  const int ncol_half = (nt / 16 + 1) / 2 * 16;
+  const int cbeg = half == 0 ? 0 : ncol_half, cend = half == 0 ? min(ncol_half, nt) : nt;
+  auto load_acc = [&](int cb, float (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    if (T > 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if ((used >> a) & 1u) {
+          float t16[16];
+          tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * nt + cb), t16);
+          const float sc = a == 3 ? (1.f / 2048.f) : 1.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(t16[i], sc, v[i]);
+        }
+      }
+    }
+  };
+  // split-K: every split writes its raw partial sums; with `counters` the LAST split to finish a tile (ticket) reduces them
+  // in fixed z order right here (deterministic: the order does not depend on which CTA happens to be last), without
+  // `counters` a separate reduce kernel does (ep_internal_splitk_reduce).
+  bool do_final = true, from_partial = false;
+  if (splits > 1) {
+    for (int cb = cbeg; cb < cend; cb += 16) {
+      float v[16];
+      load_acc(cb, v);
+      if (row < m_out) {
+        float4* dst = reinterpret_cast<float4*>(partial + ((size_t)blockIdx.z * m_out + row) * npad + col0 + cb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) __stcg(dst + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+      }
+    }
+    do_final = false;
+    if (counters) {
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        int* ctr = counters + 1 + blockIdx.y * gridDim.x + blockIdx.x;
+        const int old = atomicAdd(ctr, 1);
+        s_mask = old == splits - 1;
+        if (old == splits - 1) *ctr = 0;          // self-resetting: the buffer is all zero again when the launch retires
+      }
+      __syncthreads();
+      do_final = s_mask != 0;
+      from_partial = true;
+      if (do_final) __threadfence();
+    }
+  }
+  if (do_final) {
+    for (int cb = cbeg; cb < cend; cb += 16) {
+      float v[16];
+      if (from_partial) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        if (row < m_out) {
+          for (int z = 0; z < splits; ++z) {
+            const float4* src = reinterpret_cast<const float4*>(partial + ((size_t)z * m_out + row) * npad + col0 + cb);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 t4 = __ldcg(src + i);
+              v[4 * i] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w;
+            }
+          }
+        }
+      } else {
+        load_acc(cb, v);
+      }
+      float s[16], sq[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int col = col0 + cb + i;
+        const float val = v[i] + ((bias && col < cout) ? bias[col] : 0.f);
+        const bool ok = row < m_out && col < cout;
+        if (ok) out[(size_t)row * ld_out + col] = val;
+        s[i] = ok ? val : 0.f;
+        sq[i] = ok ? val * val : 0.f;
+      }
+      if (bn_partial) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], d);
+            sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], d);
+          }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { s_red[q][cb + i] = s[i]; s_red[4 + q][cb + i] = sq[i]; }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (bn_partial && do_final && tid < nt) {
+    const int col = col0 + tid;
+    if (col < cout) {
+      const float s = (s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]);
+      const float sq = (s_red[4][tid] + s_red[5][tid]) + (s_red[6][tid] + s_red[7][tid]);
+      const int r0 = 2 * blockIdx.x;   // bn_partial is sized for 64-row tiles: fill entry 2*bx, zero 2*bx+1
+      __stcg(&bn_partial[((size_t)r0 * 2 + 0) * cout + col], s);
+      __stcg(&bn_partial[((size_t)r0 * 2 + 1) * cout + col], sq);
+      if (r0 + 1 < bn_rows) {
+        __stcg(&bn_partial[((size_t)(r0 + 1) * 2 + 0) * cout + col], 0.f);
+        __stcg(&bn_partial[((size_t)(r0 + 1) * 2 + 1) * cout + col], 0.f);
+      }
+    }
+  }
+  // fused BatchNorm finalisation: the last tile to finish (ticket) turns the per-tile partial sums into the per-column
+  // scale / shift, summing in exactly the order of bn_finalize_kernel (csrc/spconv.cu) -- bit-identical to the separate launch.
+  if (ss_out && bn_partial && counters && do_final) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int old = atomicAdd(counters, 1);
+      const int total_tiles = gridDim.x * gridDim.y;
+      s_mask = old == total_tiles - 1;
+      if (old == total_tiles - 1) *counters = 0;
+    }
+    __syncthreads();
+    if (s_mask) {
+      __threadfence();
+      double* s_s = reinterpret_cast<double*>(smem);          // [32][33]; the operand ring is idle by now
+      double* s_q = s_s + 32 * 33;
+      const int tx = tid & 31, ty = tid >> 5;
+      for (int c0 = 0; c0 < cout; c0 += 32) {
+        const int col = c0 + tx;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int r = ty + 8 * rr;
+          double sd = 0.0, qd = 0.0;
+          if (col < cout)
+#pragma unroll 4
+            for (int b2 = r; b2 < bn_rows; b2 += 32) {
+              sd += (double)__ldcg(&bn_partial[((size_t)b2 * 2 + 0) * cout + col]);
+              qd += (double)__ldcg(&bn_partial[((size_t)b2 * 2 + 1) * cout + col]);
+            }
+          s_s[r * 33 + tx] = sd;
+          s_q[r * 33 + tx] = qd;
+        }
+        __syncthreads();
+        if (ty == 0 && col < cout) {
+          double sd = s_s[tx], qd = s_q[tx];
+#pragma unroll
+          for (int r = 1; r < 32; ++r) { sd += s_s[r * 33 + tx]; qd += s_q[r * 33 + tx]; }
+          const double mean = sd / m_out;
+          double var = qd / m_out - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float inv = (float)(1.0 / sqrt(var + (double)bn_eps));
+          const float g = gamma ? gamma[col] : 1.f, bt = beta ? beta[col] : 0.f;
+          const float sc = inv * g;
+          ss_out[col] = sc;
+          ss_out[cout + col] = bt - (float)mean * sc;
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols));
+  }
+}
+
 __device__ __forceinline__ void hl_store8(uint4* __restrict__ dst_slab_row /* 8 x uint4 */, int oct, const float (&v)[8],
                                           int* __restrict__ overflow) {
   __half h[8], l[8];
@@ -553,14 +889,21 @@ size_t ep_spconv_hl_workspace_bytes(int64_t m_out, int npad, int K) {
 // (w_hl[k][s][n][j] = fp16(W[k][32 s + j][n]), [..][32 + j] = fp16 of the remainder * 2^11; zero padded), npad = cout
 // rounded up to a multiple of 16 (of 128 when larger).  neg_row_mode 0: a missing neighbour is gathered as row m_in (first
 // out-of-bounds row), 1: as row -1.  Other arguments as ep_spconv_tc_fwd.
-int ep_spconv_hl_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t* nbr, int K, const uint16_t* w_hl, int npad,
-                     int cout, const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, void* workspace,
-                     size_t workspace_bytes, int neg_row_mode, cudaStream_t stream) {
+// Fused variant.  counters: device int32 [counters_len], all zero on entry and all zero again when the launch retires
+// (tickets; one buffer per stream), or NULL.  With counters, split-K partial sums are reduced by the last split of each tile
+// inside the conv kernel (no second launch).  ss_out (optional, float [2, cout]) receives the train-mode BatchNorm scale /
+// shift of the output columns (gamma / beta may be NULL = 1 / 0): fused into the conv kernel (last tile) for small outputs,
+// a separate ep_bn_finalize launch otherwise -- bit-identical either way.  bn_partial must be given with ss_out.
+int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t* nbr, int K, const uint16_t* w_hl, int npad,
+                           int cout, const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, void* workspace,
+                           size_t workspace_bytes, int neg_row_mode, int32_t* counters, int counters_len, const float* gamma,
+                           const float* beta, float eps, float* ss_out, cudaStream_t stream) {
   if (m_out <= 0 || m_in <= 0 || m_in > 0x7ffffff0LL || cin < 1 || cout < 1 || K < 1 || npad % 16 != 0 || npad < cout)
     return EP_ERR_ARG;
   if (!nbr && K != 1) return EP_ERR_ARG;
   if (K > 27) return EP_ERR_UNSUPPORTED;
   if (((uintptr_t)in_hl & 15) || ((uintptr_t)w_hl & 15)) return EP_ERR_ARG;
+  if (ss_out && !bn_partial) return EP_ERR_ARG;
   int nt = npad;
   if (npad > 128) {
     if (npad % 128 != 0) return EP_ERR_ARG;
@@ -569,34 +912,87 @@ int ep_spconv_hl_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t
   const int nslab = (cin + 31) / 32;
   const int tmem_cols = pow2_cols(4 * nt);
   if (tmem_cols > 512) return EP_ERR_UNSUPPORTED;
+  // operand producer: cp.async (default) or the TMA tile::gather4 path (EPRECON_HL_PRODUCER=tma; measured slower, kept as evidence)
+  static const bool use_tma = [] { const char* v = getenv("EPRECON_HL_PRODUCER"); return v && v[0] == 't'; }();
   CUtensorMap tm_a, tm_b;
-  if (!make_map(&tm_a, in_hl, (uint64_t)nslab * 64, (uint64_t)m_in, 1)) { g_hl_debug = 1; return EP_ERR_CUDA; }
+  if (use_tma && !make_map(&tm_a, in_hl, (uint64_t)nslab * 64, (uint64_t)m_in, 1)) { g_hl_debug = 1; return EP_ERR_CUDA; }
   if (!make_map(&tm_b, w_hl, 64, (uint64_t)K * nslab * npad, (uint32_t)nt)) { g_hl_debug = 2; return EP_ERR_CUDA; }
   const int stage_bytes = A_STAGE + nt * 128;
   // TMEM decides how many CTAs share an SM (512 columns): give each the deepest ring its share of shared memory allows
-  const int ctas_per_sm = 512 / tmem_cols >= 2 ? 2 : 1;
+  static const int knob_ctas = [] { const char* v = getenv("EPRECON_HL_CTAS"); return v ? atoi(v) : 0; }();
+  static const bool knob_ca = [] { const char* v = getenv("EPRECON_HL_CA"); return v && v[0] == '1'; }();
+  const int ctas_per_sm = knob_ctas == 1 ? 1 : (512 / tmem_cols >= 2 ? 2 : 1);
   // shared memory per SM: 228 KB, per CTA at most 227 KB incl. ~4.4 KB of static barriers / reduction scratch + 1 KB reserved
   const int budget = (ctas_per_sm == 2 ? 104 : 216) * 1024 - K * NBS * 4 - 1024;
   int nstage = budget / stage_bytes;
   if (nstage > MAX_STAGES) nstage = MAX_STAGES;
-  if (nstage < 2) return EP_ERR_UNSUPPORTED;
+  if (nstage < CP_LAG_MIN + 1) return EP_ERR_UNSUPPORTED;   // the cp.async producers retire a stage LAG issues later
   const size_t smem = (size_t)nstage * stage_bytes + (size_t)K * NBS * sizeof(int) + 1024;
-  static const cudaError_t attr = cudaFuncSetAttribute(spconv_hl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+  static const cudaError_t attr = [] {
+    cudaError_t e1 = cudaFuncSetAttribute(spconv_hl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaError_t e2 = cudaSuccess;
+    for (const void* f : {(const void*)spconv_hl_cp_kernel<false, 2>, (const void*)spconv_hl_cp_kernel<false, 4>,
+                          (const void*)spconv_hl_cp_kernel<false, 6>, (const void*)spconv_hl_cp_kernel<true, 2>,
+                          (const void*)spconv_hl_cp_kernel<true, 4>, (const void*)spconv_hl_cp_kernel<true, 6>}) {
+      const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+      if (e != cudaSuccess) e2 = e;
+    }
+    return e1 != cudaSuccess ? e1 : e2;
+  }();
   if (attr != cudaSuccess) { g_hl_debug = 3; return EP_ERR_CUDA; }
   const int splits = hl_splits(m_out, npad, K);
   if (splits > 1 && workspace_bytes < ep_spconv_hl_workspace_bytes(m_out, npad, K)) return EP_ERR_WORKSPACE;
   float* partial = splits > 1 ? (float*)workspace : nullptr;
   dim3 grid(ep_div_up(m_out, HTM), npad / nt, splits);
   const int bn_rows = ep_div_up(m_out, 64);
-  const int neg_row = neg_row_mode == 1 ? -1 : (int)m_in;
-  spconv_hl_kernel<<<grid, H_THREADS, smem, stream>>>(tm_a, tm_b, nbr, K, nslab, npad, nt, tmem_cols, nstage, cout, neg_row, bias,
-                                                      out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial);
-  if (splits > 1) {
-    const int s = ep_internal_splitk_reduce(partial, splits, (int)m_out, npad, cout, bias, out, ld_out, bn_partial, stream);
-    if (s != EP_OK) return s;
+  const int tiles = (int)(grid.x * grid.y);
+  int32_t* ctr = (!use_tma && counters && counters_len >= 1 + tiles) ? counters : nullptr;
+  // the finalisation runs on ONE CTA when fused: worth it while the partial-sum table is small (<= 1024 64-row tiles)
+  const bool fuse_bn = ss_out && ctr && bn_rows <= 1024;
+  if (use_tma) {
+    const int neg_row = neg_row_mode == 1 ? -1 : (int)m_in;
+    spconv_hl_kernel<<<grid, H_THREADS, smem, stream>>>(tm_a, tm_b, nbr, K, nslab, npad, nt, tmem_cols, nstage, cout, neg_row, bias,
+                                                        out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial);
+  } else {
+    // loads of LAG + 1 stages in flight per producer thread: as deep as the ring allows (LAG <= nstage - 2 keeps one stage
+    // for the tensor core to drain while the ring refills)
+    const int lag = nstage >= 8 ? 6 : (nstage >= 6 ? 4 : 2);
+#define EP_HL_LAUNCH(CA_, LAG_)                                                                                                \
+  spconv_hl_cp_kernel<CA_, LAG_><<<grid, CP_THREADS, smem, stream>>>(reinterpret_cast<const uint8_t*>(in_hl), tm_b, nbr, K, nslab, \
+                                                                     npad, nt, tmem_cols, nstage, cout, bias, out, ld_out,     \
+                                                                     (int)m_out, bn_partial, bn_rows, splits, partial, ctr,    \
+                                                                     gamma, beta, eps, fuse_bn ? ss_out : nullptr)
+    if (knob_ca) {
+      if (lag == 6) EP_HL_LAUNCH(true, 6); else if (lag == 4) EP_HL_LAUNCH(true, 4); else EP_HL_LAUNCH(true, 2);
+    } else {
+      if (lag == 6) EP_HL_LAUNCH(false, 6); else if (lag == 4) EP_HL_LAUNCH(false, 4); else EP_HL_LAUNCH(false, 2);
+    }
+#undef EP_HL_LAUNCH
+  }
+  if (splits > 1 && !ctr) {
+    const int st = ep_internal_splitk_reduce(partial, splits, (int)m_out, npad, cout, bias, out, ld_out, bn_partial, stream);
+    if (st != EP_OK) return st;
   }
   if (cudaGetLastError() != cudaSuccess) { g_hl_debug = 4; return EP_ERR_CUDA; }
+  if (ss_out && !fuse_bn) return ep_bn_finalize(bn_partial, bn_rows, cout, m_out, eps, gamma, beta, ss_out, nullptr, stream);
   return EP_OK;
+}
+
+// kernels ep_spconv_hl_fused_fwd launches for these arguments (1-3): conv [+ split-K reduce] [+ BatchNorm finalisation]
+int ep_spconv_hl_launches(int64_t m_out, int npad, int K, int have_counters, int want_ss) {
+  const int nt = npad > 128 ? 128 : npad;
+  const int splits = hl_splits(m_out, npad, K);
+  const int bn_rows = ep_div_up(m_out, 64);
+  const int tiles = ep_div_up(m_out, HTM) * (npad / nt);
+  (void)tiles;
+  return 1 + ((splits > 1 && !have_counters) ? 1 : 0) + ((want_ss && !(have_counters && bn_rows <= 1024)) ? 1 : 0);
+}
+
+int ep_spconv_hl_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t* nbr, int K, const uint16_t* w_hl, int npad,
+                     int cout, const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, void* workspace,
+                     size_t workspace_bytes, int neg_row_mode, cudaStream_t stream) {
+  return ep_spconv_hl_fused_fwd(in_hl, m_in, cin, nbr, K, w_hl, npad, cout, bias, out, ld_out, m_out, bn_partial, workspace,
+                                workspace_bytes, neg_row_mode, nullptr, 0, nullptr, nullptr, 0.f, nullptr, stream);
 }
 
 int ep_hl_debug_code(void) { return g_hl_debug; }

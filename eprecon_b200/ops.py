@@ -338,6 +338,19 @@ def _hl_weights(W, cout):
     return hit[0], hit[1]
 
 
+_COUNTERS = {}
+
+
+def _counters(dev):
+    """Zeroed int32 ticket buffer of the CURRENT stream for the fused split-K reduction of ep_spconv_hl_fused_fwd (the
+    kernels leave it zeroed; one buffer per stream so concurrent streams never share tickets)."""
+    key = (str(dev), stream_ptr())
+    t = _COUNTERS.get(key)
+    if t is None:
+        t = _COUNTERS[key] = torch.zeros(1024, dtype=torch.int32, device=dev)
+    return t
+
+
 def hl_split(x, c, overflow=None):
     """fp32 rows [m, ld] -> half-pair rows [m, nslab*64] (fp16 storage) for ep_spconv_hl_fwd."""
     m = x.shape[0]
@@ -376,9 +389,11 @@ def spconv(x, cin, nbr, W, cout, bias=None, m_out=None, want_stats=False, out=No
         x_hl = hl_split(x, cin)
         wsb = L.ep_spconv_hl_workspace_bytes(m_out, npad, K)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
-        _lib.check(L.ep_spconv_hl_fwd(x_hl.data_ptr(), x.shape[0], cin, _ptr(nbr), K, w_hl.data_ptr(), npad, cout,
-                                      _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
-                                      _ptr(ws), wsb, HL_NEG_ROW_MODE, stream_ptr()), "ep_spconv_hl_fwd")
+        ctr = _counters(dev)
+        _lib.check(L.ep_spconv_hl_fused_fwd(x_hl.data_ptr(), x.shape[0], cin, _ptr(nbr), K, w_hl.data_ptr(), npad, cout,
+                                            _ptr(bias), out.data_ptr() + 4 * out_col, out.stride(0), m_out, _ptr(part),
+                                            _ptr(ws), wsb, HL_NEG_ROW_MODE, ctr.data_ptr(), ctr.numel(), 0, 0, 0.0, 0,
+                                            stream_ptr()), "ep_spconv_hl_fused_fwd")
     else:
         prec = 3 if SPCONV_IMPL == "tf32x3" else 1
         w_hi, w_lo, npad = _umma_weights(W, cout, prec)

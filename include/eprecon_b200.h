@@ -130,6 +130,11 @@ size_t ep_spconv_hl_workspace_bytes(int64_t m_out, int npad, int K);
 int ep_spconv_hl_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t* nbr, int K, const uint16_t* w_hl, int npad,
                      int cout, const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, void* workspace,
                      size_t workspace_bytes, int neg_row_mode, cudaStream_t stream);
+int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t* nbr, int K, const uint16_t* w_hl, int npad,
+                           int cout, const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, void* workspace,
+                           size_t workspace_bytes, int neg_row_mode, int32_t* counters, int counters_len, const float* gamma,
+                           const float* beta, float eps, float* ss_out, cudaStream_t stream);
+int ep_spconv_hl_launches(int64_t m_out, int npad, int K, int have_counters, int want_ss);
 int ep_hl_debug_code(void);   /* last failure site of ep_spconv_hl_fwd: 1 map A, 2 map B, 3 smem attribute, 4 launch */
 int ep_hl_probe_gather4(const uint16_t* in_hl, int64_t m_in, int nslab, const int32_t* rows128, int slab, void* out16k,
                         int32_t* status, cudaStream_t stream);

@@ -20,6 +20,14 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
+def elem(a, b, floor):
+    """worst |a-b| / (1e-3 * max(|b|, floor * max|b|)): <= 1 means every entry at least `floor` of the tensor's scale is
+    within 1e-3 of ITSELF (the smaller ones are bounded by 1e-3 * floor * scale)."""
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    bound = 1e-3 * torch.maximum(b.abs(), floor * b.abs().max())
+    return float(((a - b).abs() / bound).max())
+
+
 def main():
     full = "--full" in sys.argv
     if full:
@@ -43,7 +51,8 @@ def main():
     cin = {k: (v.cuda() if torch.is_tensor(v) else ([t.cuda() for t in v] if isinstance(v, list) and torch.is_tensor(v[0]) else v))
            for k, v in inputs.items()}
     fa_c, fb_c = [[t.cuda() for t in f] for f in fa], [[t.cuda() for t in f] for f in fb]
-    for impl in ("ffma", "tf32x3", "tf32"):
+    impls = [a for a in sys.argv[1:] if not a.startswith("--")] or ["ffma", "tf32x3", "hl", "tf32"]
+    for impl in impls:
         ops.SPCONV_IMPL = impl
         cin["scene"] = [f"scene_{impl}"]
         net.trace, net.teacher = {}, ot
@@ -62,6 +71,15 @@ def main():
             rep[f"l{lv}_mask_flips"] = int((a["occupancy"].cpu() != b["occupancy"]).sum())
         rep["final_coords_exact"] = bool(torch.equal(out["coords"].cpu(), oout["coords"]))
         rep["final_tsdf"] = rel(out["tsdf"], oout["tsdf"])
+        # elementwise view (worst ratio to the bound) at three floors, over every float stage
+        pairs = [("init_occ", t["init"]["occ"], ot["init"]["occ"]), ("final_tsdf", out["tsdf"], oout["tsdf"])]
+        for lv in range(3):
+            pairs += [(f"l{lv}_spvcnn", t[f"l{lv}_pre_gru"]["spvcnn"], ot[f"l{lv}_pre_gru"]["spvcnn"]),
+                      (f"l{lv}_gru", t[f"l{lv}"]["feat_all"], ot[f"l{lv}"]["feat_all"]),
+                      (f"l{lv}_tsdf", t[f"l{lv}"]["tsdf"], ot[f"l{lv}"]["tsdf"]), (f"l{lv}_occ", t[f"l{lv}"]["occ"], ot[f"l{lv}"]["occ"])]
+        for floor in (0.01, 0.05, 0.25):
+            worst = max((elem(a, b, floor), name) for name, a, b in pairs)
+            rep[f"elementwise_worst@floor{floor}"] = [round(worst[0], 3), worst[1]]
         print(json.dumps(rep))
 
 
