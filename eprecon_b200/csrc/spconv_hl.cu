@@ -331,17 +331,19 @@ hl_split_kernel(const float* __restrict__ src, int ld, int c, long long m, int n
 // lanes per 128-byte row, so a warp instruction moves 4 whole rows (4 L1TEX wavefronts for 512 bytes).
 constexpr int CP_THREADS = 256;            // warps 0-3: cp.async producers, warp 4 lane 0: MMA issuer, all 8 warps: epilogue
 constexpr int CP_PRODUCERS = 128;
-constexpr int CP_LAG_MIN = 2;              // a thread keeps the loads of LAG + 1 stages in flight (template parameter)
-
-template <bool CA>
+// Completion: every producer thread issues `cp.async.mbarrier.arrive.noinc` on the stage's full-barrier right after its
+// copies -- the barrier receives that arrival when the thread's copies have landed -- and moves on to the next stage at once
+// (the same protocol as CUTLASS's sm100 cp.async/UMMA mainloop).  The first version retired stages with cp.async.wait_group +
+// fence.proxy.async + arrive in the producer: the proxy fence drains ALL of the thread's outstanding copies, i.e. one stage
+// in flight per thread, and the kernel ran at 1 / (memory latency) per CTA (profiles/r02_probe_hl_v2_cpasync_fence_timing.json:
+// 1 CTA per SM with an 8-deep ring was 1.75x SLOWER than 2 CTAs with 4 stages).  `.ca` instead of `.cg` made no difference.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  if (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-  else asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// CA: gathered chunks allocate in L1 (a tile re-gathers each of its ~370 distinct rows ~9 times over the 27 offsets) or bypass
-// it; CP_LAG: ring depth in flight per thread.
-template <bool CA, int CP_LAG>
 __global__ void __launch_bounds__(CP_THREADS)
 spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ CUtensorMap tm_b,
                     const int* __restrict__ nbr, int K, int nslab, int npad, int nt, int tmem_cols, int nstage, int cout,
@@ -429,35 +431,26 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
       }
     };
     if (T > 0) set_k();
-    int stage = 0, round = 0;          // issue cursor
-    int rstage = 0;                    // retire cursor
-    for (int t = 0; t < T + CP_LAG; ++t) {
-      if (t < T) {
-        if (round > 0) mbar_wait_b(&empty_bar[stage], (round - 1) & 1);
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        if (tid == 0) {
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_stage);
-          tma_tile2d(&tm_b, &full_bar[stage], smem + (size_t)stage * stage_bytes + A_STAGE, 0, (k * nslab + c) * npad + col0);
-        }
+    int stage = 0, round = 0;
+    for (int t = 0; t < T; ++t) {
+      if (round > 0) mbar_wait_b(&empty_bar[stage], (round - 1) & 1);
+      const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_stage);
+        tma_tile2d(&tm_b, &full_bar[stage], smem + (size_t)stage * stage_bytes + A_STAGE, 0, (k * nslab + c) * npad + col0);
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint8_t* p = rowp[i];
-          cp_async16<CA>(sa + dst_thread + i * (16 * 128), p ? p + c * 128 : in_hl, p ? 16u : 0u);   // missing neighbour: zero fill
-        }
-        if (++c == nslab) {
-          c = 0;
-          rem &= rem - 1;
-          if (rem) set_k();
-        }
-        if (++stage == nstage) { stage = 0; ++round; }
+      for (int i = 0; i < 8; ++i) {
+        const uint8_t* p = rowp[i];
+        cp_async16(sa + dst_thread + i * (16 * 128), p ? p + c * 128 : in_hl, p ? 16u : 0u);   // missing neighbour: zero fill
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");          // (empty groups past the end keep the wait depth uniform)
-      if (t >= CP_LAG) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(CP_LAG) : "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
-        mbar_arrive(&full_bar[rstage]);
-        if (++rstage == nstage) rstage = 0;
+      cp_async_arrive_noinc(&full_bar[stage]);    // arrives once this thread's copies (of this and earlier stages) have landed
+      if (++c == nslab) {
+        c = 0;
+        rem &= rem - 1;
+        if (rem) set_k();
       }
+      if (++stage == nstage) { stage = 0; ++round; }
     }
   } else if (warp == 4 && lane == 0) {
     // ------------------------------------------------------------- MMA issuer (one thread)
@@ -466,6 +459,7 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
     int stage = 0, round = 0;
     for (int t = 0; t < T; ++t) {
       mbar_wait_b(&full_bar[stage], round & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // belt and braces (one thread): cp.async data -> async proxy
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + A_STAGE;
 #pragma unroll
@@ -920,23 +914,16 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
   const int stage_bytes = A_STAGE + nt * 128;
   // TMEM decides how many CTAs share an SM (512 columns): give each the deepest ring its share of shared memory allows
   static const int knob_ctas = [] { const char* v = getenv("EPRECON_HL_CTAS"); return v ? atoi(v) : 0; }();
-  static const bool knob_ca = [] { const char* v = getenv("EPRECON_HL_CA"); return v && v[0] == '1'; }();
   const int ctas_per_sm = knob_ctas == 1 ? 1 : (512 / tmem_cols >= 2 ? 2 : 1);
   // shared memory per SM: 228 KB, per CTA at most 227 KB incl. ~4.4 KB of static barriers / reduction scratch + 1 KB reserved
   const int budget = (ctas_per_sm == 2 ? 104 : 216) * 1024 - K * NBS * 4 - 1024;
   int nstage = budget / stage_bytes;
   if (nstage > MAX_STAGES) nstage = MAX_STAGES;
-  if (nstage < CP_LAG_MIN + 1) return EP_ERR_UNSUPPORTED;   // the cp.async producers retire a stage LAG issues later
+  if (nstage < 2) return EP_ERR_UNSUPPORTED;
   const size_t smem = (size_t)nstage * stage_bytes + (size_t)K * NBS * sizeof(int) + 1024;
   static const cudaError_t attr = [] {
     cudaError_t e1 = cudaFuncSetAttribute(spconv_hl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    cudaError_t e2 = cudaSuccess;
-    for (const void* f : {(const void*)spconv_hl_cp_kernel<false, 2>, (const void*)spconv_hl_cp_kernel<false, 4>,
-                          (const void*)spconv_hl_cp_kernel<false, 6>, (const void*)spconv_hl_cp_kernel<true, 2>,
-                          (const void*)spconv_hl_cp_kernel<true, 4>, (const void*)spconv_hl_cp_kernel<true, 6>}) {
-      const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-      if (e != cudaSuccess) e2 = e;
-    }
+    cudaError_t e2 = cudaFuncSetAttribute(spconv_hl_cp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     return e1 != cudaSuccess ? e1 : e2;
   }();
   if (attr != cudaSuccess) { g_hl_debug = 3; return EP_ERR_CUDA; }
@@ -954,20 +941,10 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
     spconv_hl_kernel<<<grid, H_THREADS, smem, stream>>>(tm_a, tm_b, nbr, K, nslab, npad, nt, tmem_cols, nstage, cout, neg_row, bias,
                                                         out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial);
   } else {
-    // loads of LAG + 1 stages in flight per producer thread: as deep as the ring allows (LAG <= nstage - 2 keeps one stage
-    // for the tensor core to drain while the ring refills)
-    const int lag = nstage >= 8 ? 6 : (nstage >= 6 ? 4 : 2);
-#define EP_HL_LAUNCH(CA_, LAG_)                                                                                                \
-  spconv_hl_cp_kernel<CA_, LAG_><<<grid, CP_THREADS, smem, stream>>>(reinterpret_cast<const uint8_t*>(in_hl), tm_b, nbr, K, nslab, \
-                                                                     npad, nt, tmem_cols, nstage, cout, bias, out, ld_out,     \
-                                                                     (int)m_out, bn_partial, bn_rows, splits, partial, ctr,    \
-                                                                     gamma, beta, eps, fuse_bn ? ss_out : nullptr)
-    if (knob_ca) {
-      if (lag == 6) EP_HL_LAUNCH(true, 6); else if (lag == 4) EP_HL_LAUNCH(true, 4); else EP_HL_LAUNCH(true, 2);
-    } else {
-      if (lag == 6) EP_HL_LAUNCH(false, 6); else if (lag == 4) EP_HL_LAUNCH(false, 4); else EP_HL_LAUNCH(false, 2);
-    }
-#undef EP_HL_LAUNCH
+    spconv_hl_cp_kernel<<<grid, CP_THREADS, smem, stream>>>(reinterpret_cast<const uint8_t*>(in_hl), tm_b, nbr, K, nslab, npad, nt,
+                                                            tmem_cols, nstage, cout, bias, out, ld_out, (int)m_out, bn_partial,
+                                                            bn_rows, splits, partial, ctr, gamma, beta, eps,
+                                                            fuse_bn ? ss_out : nullptr);
   }
   if (splits > 1 && !ctr) {
     const int st = ep_internal_splitk_reduce(partial, splits, (int)m_out, npad, cout, bias, out, ld_out, bn_partial, stream);

@@ -281,8 +281,9 @@ def kmap_build(out_coords, batch_first, offsets, table, shape=None):
 # back-projection: "fused" = single-pass kernel (count + look-back compaction + gather), "3pass" = count / compact / gather
 BP_IMPL = os.environ.get("EPRECON_BP", "fused")
 
-# "ffma" = fp32 CUDA-core gather-GEMM (csrc/spconv.cu); "tf32x3" / "tf32" = tcgen05 tensor-core kernel (csrc/spconv_tc.cu)
-SPCONV_IMPL = os.environ.get("EPRECON_SPCONV", "tf32x3")
+# "hl" (default) = tcgen05 kind::f16 on pre-split half-pair operands gathered by cp.async (csrc/spconv_hl.cu); "tf32x3" / "tf32" =
+# the round-1 tcgen05 kind::tf32 kernel with register producers (csrc/spconv_tc.cu); "ffma" = fp32 CUDA-core gather-GEMM (csrc/spconv.cu)
+SPCONV_IMPL = os.environ.get("EPRECON_SPCONV", "hl")
 _UMMA_CACHE = {}
 
 

@@ -5,7 +5,7 @@ restatement).
   * configs[1] (96^3, 9 x 640 x 480, the bench fragment: ~210 k level-2 candidates, ~105 k final voxels):
       - a 3-fragment stream of ONE scene through the recurrent GRU state, teacher-forced on the oracle's data-dependent
         decisions, stage by stage: voxel sets / union sites / aligned points bit-exact, floats within 1e-3 in the max
-        norm AND elementwise (|a-b| <= 1e-3 * max(|b|, 1e-2 * max|b|));
+        norm AND elementwise (|a-b| <= 1e-3 * max(|b|, 0.25 * max|b|), see elementwise_ok);
       - the first fragment free-running (no teacher): at most 2e-4 of the final voxels may differ, every one of them
         within 1e-4 of its occupancy threshold, TSDF on the common voxels within 1e-3.
   * configs[4] (128^3, 18 x 960 x 720), one fragment, TSDF path, shipped caps (config/test.yaml:29): teacher-forced,
