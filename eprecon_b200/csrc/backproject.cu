@@ -384,50 +384,31 @@ bp_fused_kernel(const int4* __restrict__ coords, int n, const float* __restrict_
   __syncthreads();
   const int tile = s_tile;
   const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-  // ---- phase A: one lane per (voxel, view).  A warp owns TV / 8 voxels and walks them 32 / V at a time; the views of a
-  //      voxel sit in consecutive lanes, so ONE __ballot_sync yields the voxel's visibility mask (no shared-memory atomics).
-  //      Exact-arithmetic short cut: the reference's test  |fl(fl(2 fl(X/Z)) / (W-1)) - 1| <= 1 & Z > 0  can only hold when
-  //      Z > 0 and -eps (W-1) Z <= X <= (1 + eps)(W-1) Z (eps = 1e-4 >> the few ulps of the rounded chain), likewise for Y:
-  //      a (voxel, view) outside that band is invisible without a single division; inside the band the full IEEE chain
-  //      (4 divisions) decides, bit for bit as before.  On shells ~2.4 of 9 views survive the band.
+  // (A lane-per-(voxel, view) variant with a division-free rejection band and a __ballot_sync mask was measured in round 2:
+  //  1457 us vs 950 us on the batched probe -- the band only pays when whole warps skip the divisions, and with ~27 % of
+  //  the (voxel, view) pairs visible almost every warp still runs them, while the three dependent passes per warp expose the
+  //  coordinate-load latency three times.  Kept: the exact power-of-two scaling of the sample position.)
+  // ---- phase A: thread (vox = t % TV, part = t / TV) projects views part, part+4, ... of its voxel
   {
-    const int lane_a = t & 31, warp_a = t >> 5;
-    constexpr int VOX_PER_WARP = TV / (FT / 32);
-    const int vpp = 32 / V;                               // voxels per pass (V <= 32)
-    const int slot = lane_a / V, v = lane_a - slot * V;
-    const float eps = 1e-4f;
-    for (int j0 = 0; j0 < VOX_PER_WARP; j0 += vpp) {
-      const int j = j0 + slot;
-      const int vox = warp_a * VOX_PER_WARP + j;
-      const int i = tile * TV + vox;
-      const bool on = slot < vpp && j < VOX_PER_WARP && i < n;
-      bool vis = false;
-      if (on) {
-        const int4 c = coords[i];
-        if (v == 0) s_coord[vox] = c;
-        float wx, wy, wz;
-        world_point(c.y, c.z, c.w, vs, origin + 3 * c.x, wx, wy, wz);
-        const float* P = s_kr + (v * bs + c.x) * 16;
-        const float X = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[0], wx), __fmul_rn(P[1], wy)), __fmul_rn(P[2], wz)), P[3]);
-        const float Y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[4], wx), __fmul_rn(P[5], wy)), __fmul_rn(P[6], wz)), P[7]);
-        const float Z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[8], wx), __fmul_rn(P[9], wy)), __fmul_rn(P[10], wz)), P[11]);
-        const float bx = wm1 * Z, by = hm1 * Z;
-        const bool band = Z > 0.f && X >= -eps * bx && X <= bx + eps * bx && Y >= -eps * by && Y <= by + eps * by;
-        if (band) {
-          const float u = __fdiv_rn(X, Z), w_ = __fdiv_rn(Y, Z);
-          const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, u), wm1), 1.f);
-          const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, w_), hm1), 1.f);
-          vis = (fabsf(gx) <= 1.f) && (fabsf(gy) <= 1.f);
-          if (vis) {
-            // (g + 1) / 2 is an exact scaling by a power of two: the multiplication by 0.5 is bit-identical to the division
-            s_pos[v * TV + vox] = make_float2(__fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), wm1),
-                                              __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), hm1));
-            if (zbar) s_z[v * TV + vox] = Z;
-          }
+    const int vox = t & (TV - 1), part = t / TV;
+    const int i = tile * TV + vox;
+    if (i < n) {
+      const int4 c = coords[i];
+      if (part == 0) s_coord[vox] = c;
+      float wx, wy, wz;
+      world_point(c.y, c.z, c.w, vs, origin + 3 * c.x, wx, wy, wz);
+      uint32_t m = 0;
+      for (int v = part; v < V; v += FT / TV) {
+        ProjOut p = project_one(s_kr + (v * bs + c.x) * 16, wx, wy, wz, wm1, hm1);
+        if (p.vis) {
+          m |= 1u << v;
+          // (g + 1) / 2 is an exact scaling by a power of two: multiplying by 0.5 is bit-identical to the division
+          s_pos[v * TV + vox] = make_float2(__fmul_rn(__fmul_rn(__fadd_rn(p.gx, 1.f), 0.5f), wm1),
+                                            __fmul_rn(__fmul_rn(__fadd_rn(p.gy, 1.f), 0.5f), hm1));
+          if (zbar) s_z[v * TV + vox] = p.z;
         }
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, vis);
-      if (on && v == 0) s_mask[vox] = (bal >> (slot * V)) & (V == 32 ? 0xffffffffu : ((1u << V) - 1u));
+      if (m) atomicOr(&s_mask[vox], m);
     }
   }
   __syncthreads();

@@ -78,6 +78,7 @@ __device__ __forceinline__ void tma_tile2d(const CUtensorMap* map, uint64_t* bar
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   const long long t0 = clock64();
+  uint32_t spins = 0;
   for (;;) {
     uint32_t done;
     asm volatile(
@@ -88,7 +89,7 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
 
@@ -337,20 +338,24 @@ constexpr int CP_PRODUCERS = 128;
 // fence.proxy.async + arrive in the producer: the proxy fence drains ALL of the thread's outstanding copies, i.e. one stage
 // in flight per thread, and the kernel ran at 1 / (memory latency) per CTA (profiles/r02_probe_hl_v2_cpasync_fence_timing.json:
 // 1 CTA per SM with an 8-deep ring was 1.75x SLOWER than 2 CTAs with 4 stages).  `.ca` instead of `.cg` made no difference.
+template <bool CA>
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  if (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  else asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+template <bool CA>
 __global__ void __launch_bounds__(CP_THREADS)
 spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ CUtensorMap tm_b,
                     const int* __restrict__ nbr, int K, int nslab, int npad, int nt, int tmem_cols, int nstage, int cout,
                     const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m_out,
                     float* __restrict__ bn_partial, int bn_rows, int splits, float* __restrict__ partial,
                     int* __restrict__ counters /* zeroed tickets: [0] finished tiles, [1 + tile] finished splits; or null */,
-                    const float* __restrict__ gamma, const float* __restrict__ beta, float bn_eps, float* __restrict__ ss_out) {
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float bn_eps, float* __restrict__ ss_out,
+                    long long* __restrict__ dbg /* optional timeline of one CTA: [stage][6] clock64 stamps */) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int b_stage = nt * 128;
@@ -366,6 +371,7 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
   const int row0 = blockIdx.x * HTM;
   const int col0 = blockIdx.y * nt;
   const int kb = (int)(((long long)blockIdx.z * K) / splits), ke = (int)(((long long)(blockIdx.z + 1) * K) / splits);
+  if (dbg && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) dbg[6 * 64 + 2] = clock64();
 
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
@@ -383,7 +389,7 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   {
-    constexpr int PU = 4;
+    constexpr int PU = 14;      // 128 x 27 / 256 threads: every load of the tile's neighbour slab is in flight at once
     const int total = HTM * K;
     const long long base = (long long)row0 * K, lim = (long long)m_out * K;
     unsigned mine = 0;
@@ -432,8 +438,11 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
     };
     if (T > 0) set_k();
     int stage = 0, round = 0;
+    const bool rec = dbg && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
     for (int t = 0; t < T; ++t) {
+      if (rec && t < 64) dbg[6 * t + 0] = clock64();
       if (round > 0) mbar_wait_b(&empty_bar[stage], (round - 1) & 1);
+      if (rec && t < 64) dbg[6 * t + 1] = clock64();
       const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
       if (tid == 0) {
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_stage);
@@ -442,9 +451,10 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint8_t* p = rowp[i];
-        cp_async16(sa + dst_thread + i * (16 * 128), p ? p + c * 128 : in_hl, p ? 16u : 0u);   // missing neighbour: zero fill
+        cp_async16<CA>(sa + dst_thread + i * (16 * 128), p ? p + c * 128 : in_hl, p ? 16u : 0u);   // missing neighbour: zero fill
       }
       cp_async_arrive_noinc(&full_bar[stage]);    // arrives once this thread's copies (of this and earlier stages) have landed
+      if (rec && t < 64) dbg[6 * t + 2] = clock64();
       if (++c == nslab) {
         c = 0;
         rem &= rem - 1;
@@ -452,34 +462,50 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
       }
       if (++stage == nstage) { stage = 0; ++round; }
     }
-  } else if (warp == 4 && lane == 0) {
-    // ------------------------------------------------------------- MMA issuer (one thread)
+  } else if (warp == 4) {
+    // ------------------------------------------------------------- MMA issuer: warp 4 stays converged, one elected lane issues
+    // (a divergent `if (lane == 0)` makes the compiler wrap every UTCHMMA in an ELECT / BRA.U.ANY loop; the first version also
+    //  ran a proxy fence = MEMBAR.ALL.CTA per stage here: ~600 cycles to issue 6 MMAs, the bottleneck of the whole kernel,
+    //  profiles/r02_timeline_hl_v3.json)
     const uint32_t idesc = (1u << 4) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(HTM >> 4) << 24);   // f16 x f16 -> f32
+    // descriptors differ only in their 14-bit start-address field: base + stage * (stage_bytes >> 4) + {0,2,4,6} (32-byte k steps)
+    const uint64_t da0 = umma_desc_sw128(smem_u32(smem)), db0 = umma_desc_sw128(smem_u32(smem) + A_STAGE);
+    const uint32_t dstep = (uint32_t)stage_bytes >> 4;
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
     uint32_t used = 0;
     int stage = 0, round = 0;
+    const bool rec = dbg && elected && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
     for (int t = 0; t < T; ++t) {
+      if (rec && t < 64) dbg[6 * t + 3] = clock64();
       mbar_wait_b(&full_bar[stage], round & 1);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // belt and braces (one thread): cp.async data -> async proxy
+      if (rec && t < 64) dbg[6 * t + 4] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + A_STAGE;
+      if (elected) {
+        const uint64_t da = da0 + (uint64_t)(stage * dstep), db = db0 + (uint64_t)(stage * dstep);
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const uint64_t dah = umma_desc_sw128(sa + kk * 32), dal = umma_desc_sw128(sa + 64 + kk * 32);
-        const uint64_t dbh = umma_desc_sw128(sb + kk * 32), dbl = umma_desc_sw128(sb + 64 + kk * 32);
-        const int am = (t * 2 + kk) % 3;
-        umma_f16(tmem_d + am * nt, dah, dbh, idesc, (used >> am) & 1u);
-        used |= 1u << am;
-        umma_f16(tmem_d + 3 * nt, dal, dbh, idesc, (used >> 3) & 1u);
-        used |= 1u << 3;
-        umma_f16(tmem_d + 3 * nt, dah, dbl, idesc, 1u);
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint64_t dah = da + 2 * kk, dal = da + 4 + 2 * kk, dbh = db + 2 * kk, dbl = db + 4 + 2 * kk;
+          const int am = (t * 2 + kk) % 3;
+          umma_f16(tmem_d + am * nt, dah, dbh, idesc, (used >> am) & 1u);
+          used |= 1u << am;
+          umma_f16(tmem_d + 3 * nt, dal, dbh, idesc, (used >> 3) & 1u);
+          used |= 1u << 3;
+          umma_f16(tmem_d + 3 * nt, dah, dbl, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);
       }
-      umma_commit(&empty_bar[stage]);
+      __syncwarp();
+      if (rec && t < 64) dbg[6 * t + 5] = clock64();
       if (++stage == nstage) { stage = 0; ++round; }
     }
-    umma_commit(&all_done);
-    s_used = (int)used;
+    if (elected) {
+      umma_commit(&all_done);
+      s_used = (int)used;
+    }
   }
   __syncthreads();
+  if (dbg && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) dbg[6 * 64] = clock64();
   // ------------------------------------------------------------- epilogue: warp w owns TMEM lanes 32 (w & 3) and one half of the columns
   if (T > 0) mbar_wait_b(&all_done, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -645,6 +671,7 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
       }
     }
   }
+  if (dbg && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) dbg[6 * 64 + 1] = clock64();
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols));
   }
@@ -812,6 +839,7 @@ bool make_map(CUtensorMap* map, const void* base, uint64_t row_halfs, uint64_t r
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+long long* g_hl_timeline = nullptr;   // device buffer [6 * 64 + 3] set by ep_hl_set_timeline (debug)
 int g_hl_debug = 0;   // last failure site of ep_spconv_hl_fwd (1 map A, 2 map B, 3 smem attribute, 4 launch); ep_hl_debug_code()
 
 inline int pow2_cols(int n) {
@@ -914,17 +942,22 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
   const int stage_bytes = A_STAGE + nt * 128;
   // TMEM decides how many CTAs share an SM (512 columns): give each the deepest ring its share of shared memory allows
   static const int knob_ctas = [] { const char* v = getenv("EPRECON_HL_CTAS"); return v ? atoi(v) : 0; }();
-  const int ctas_per_sm = knob_ctas == 1 ? 1 : (512 / tmem_cols >= 2 ? 2 : 1);
+  // CTAs per SM: as many as TMEM allows, up to 3 -- the LSU's cp.async rate (~17 cycles per 512-byte gather instruction per SM)
+  // bounds the main loop, and only OTHER CTAs' main loops can fill the prologue / epilogue bubbles of a tile (2 -> 3 CTAs:
+  // -20 % on the level-2 convs even though the ring shrinks from 4 to 2 stages; profiles/r02_probe_hl_v4_*)
+  int ctas_per_sm = 512 / tmem_cols >= 3 ? 3 : (512 / tmem_cols >= 2 ? 2 : 1);
+  if (knob_ctas >= 1 && knob_ctas <= 3 && 512 / tmem_cols >= knob_ctas) ctas_per_sm = knob_ctas;
   // shared memory per SM: 228 KB, per CTA at most 227 KB incl. ~4.4 KB of static barriers / reduction scratch + 1 KB reserved
-  const int budget = (ctas_per_sm == 2 ? 104 : 216) * 1024 - K * NBS * 4 - 1024;
+  const int budget = (ctas_per_sm >= 4 ? 50 : ctas_per_sm == 3 ? 68 : ctas_per_sm == 2 ? 104 : 216) * 1024 - K * NBS * 4 - 1024;
   int nstage = budget / stage_bytes;
   if (nstage > MAX_STAGES) nstage = MAX_STAGES;
   if (nstage < 2) return EP_ERR_UNSUPPORTED;
   const size_t smem = (size_t)nstage * stage_bytes + (size_t)K * NBS * sizeof(int) + 1024;
   static const cudaError_t attr = [] {
     cudaError_t e1 = cudaFuncSetAttribute(spconv_hl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    cudaError_t e2 = cudaFuncSetAttribute(spconv_hl_cp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    return e1 != cudaSuccess ? e1 : e2;
+    cudaError_t e2 = cudaFuncSetAttribute(spconv_hl_cp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaError_t e3 = cudaFuncSetAttribute(spconv_hl_cp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    return e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
   }();
   if (attr != cudaSuccess) { g_hl_debug = 3; return EP_ERR_CUDA; }
   const int splits = hl_splits(m_out, npad, K);
@@ -941,10 +974,17 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
     spconv_hl_kernel<<<grid, H_THREADS, smem, stream>>>(tm_a, tm_b, nbr, K, nslab, npad, nt, tmem_cols, nstage, cout, neg_row, bias,
                                                         out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial);
   } else {
-    spconv_hl_cp_kernel<<<grid, CP_THREADS, smem, stream>>>(reinterpret_cast<const uint8_t*>(in_hl), tm_b, nbr, K, nslab, npad, nt,
-                                                            tmem_cols, nstage, cout, bias, out, ld_out, (int)m_out, bn_partial,
-                                                            bn_rows, splits, partial, ctr, gamma, beta, eps,
-                                                            fuse_bn ? ss_out : nullptr);
+    static const bool knob_ca = [] { const char* v = getenv("EPRECON_HL_CA"); return v && v[0] == '1'; }();
+    if (knob_ca)
+      spconv_hl_cp_kernel<true><<<grid, CP_THREADS, smem, stream>>>(reinterpret_cast<const uint8_t*>(in_hl), tm_b, nbr, K, nslab, npad, nt,
+                                                                    tmem_cols, nstage, cout, bias, out, ld_out, (int)m_out, bn_partial,
+                                                                    bn_rows, splits, partial, ctr, gamma, beta, eps,
+                                                                    fuse_bn ? ss_out : nullptr, g_hl_timeline);
+    else
+      spconv_hl_cp_kernel<false><<<grid, CP_THREADS, smem, stream>>>(reinterpret_cast<const uint8_t*>(in_hl), tm_b, nbr, K, nslab, npad, nt,
+                                                                     tmem_cols, nstage, cout, bias, out, ld_out, (int)m_out, bn_partial,
+                                                                     bn_rows, splits, partial, ctr, gamma, beta, eps,
+                                                                     fuse_bn ? ss_out : nullptr, g_hl_timeline);
   }
   if (splits > 1 && !ctr) {
     const int st = ep_internal_splitk_reduce(partial, splits, (int)m_out, npad, cout, bias, out, ld_out, bn_partial, stream);
@@ -973,6 +1013,11 @@ int ep_spconv_hl_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const int32_t
 }
 
 int ep_hl_debug_code(void) { return g_hl_debug; }
+
+// debug: device int64 [6 * 64 + 3] that receives the clock64 timeline of the middle CTA of every following launch (NULL = off):
+// per stage t: producer {wait-empty begin, end, copies issued}, MMA thread {wait-full begin, end, MMAs issued + committed};
+// then [384] main loop done, [385] epilogue done, [386] kernel entry
+int ep_hl_set_timeline(void* dev_buffer) { g_hl_timeline = (long long*)dev_buffer; return EP_OK; }
 
 // Debug entry: gathers the 128 rows `rows128` (device int32[128]; any value, out-of-range rows must read as zeros) of slab
 // `slab` of in_hl [m_in][nslab][64] with 32 gather4 and returns the raw shared-memory image (16 KB) + status (1 ok, -1 timeout).

@@ -135,6 +135,7 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
                            size_t workspace_bytes, int neg_row_mode, int32_t* counters, int counters_len, const float* gamma,
                            const float* beta, float eps, float* ss_out, cudaStream_t stream);
 int ep_spconv_hl_launches(int64_t m_out, int npad, int K, int have_counters, int want_ss);
+int ep_hl_set_timeline(void* dev_buffer);   /* debug: clock64 timeline of one CTA of every following ep_spconv_hl launch */
 int ep_hl_debug_code(void);   /* last failure site of ep_spconv_hl_fwd: 1 map A, 2 map B, 3 smem attribute, 4 launch */
 int ep_hl_probe_gather4(const uint16_t* in_hl, int64_t m_in, int nslab, const int32_t* rows128, int slab, void* out16k,
                         int32_t* status, cudaStream_t stream);
@@ -202,6 +203,19 @@ size_t ep_masked_attention_workspace_bytes(int64_t n_keys, int n_heads);
 int ep_masked_attention(const float* q, const float* k, const float* v, int ld_kv, const uint8_t* blocked, int64_t n_keys,
                         int n_queries, int n_heads, int head_dim, float scale, float* out, void* workspace,
                         size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- scene TSDF -> mesh: GPU marching cubes + nearest-voxel labels, replaces the CPU tail of the reference's
+ * mesh export (utils.py:231-247 skimage.measure.marching_cubes + np.round / np.clip lookup; volumes from gru_fusion.py:217-257).
+ * vol f32 [dx,dy,dz]; edge_flags uint8 [3*n] (3 * voxel + axis: the surface crosses the grid edge leaving the voxel along
+ * +axis -> one mesh vertex); cell_ntri uint8 [n]; vertices / faces are written at offsets from stable compactions / scans of
+ * those, so their order is deterministic.  Case table: csrc/mc_table.cuh (derived by tools/gen_mc_table.py). */
+int ep_mc_classify(const float* vol, int dx, int dy, int dz, float level, uint8_t* edge_flags, uint8_t* cell_ntri,
+                   cudaStream_t stream);
+int ep_mc_vertices(const float* vol, int dx, int dy, int dz, float level, const int32_t* edge_index, int64_t n_verts, float* verts,
+                   float* normals, const int32_t* sem_vol, const int32_t* inst_vol, int32_t* sem_out, int32_t* inst_out,
+                   cudaStream_t stream);
+int ep_mc_faces(const float* vol, int dx, int dy, int dz, float level, const int32_t* cell_index, const int32_t* tri_offset,
+                int64_t n_cells, const int32_t* edge_pos, int32_t* faces, cudaStream_t stream);
 
 /* ---- small index helpers used by the native executor --------------------------------------------------------
  * ep_csr_expand: segments of a (voxel id)-keyed sort -> dense per-voxel [s0, s1) ranges (s0/s1 pre-zeroed; the scatter

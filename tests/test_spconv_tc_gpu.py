@@ -1,4 +1,5 @@
-"""tcgen05 tensor-core sparse conv (csrc/spconv_tc.cu) vs the fp32 CUDA-core kernel and the CPU oracle."""
+"""tcgen05 tensor-core sparse convs (csrc/spconv_hl.cu: half-pair operands, cp.async gather; csrc/spconv_tc.cu: 3xTF32, register
+producers) vs the fp32 CUDA-core kernel and fp64."""
 import pytest
 import torch
 
@@ -48,7 +49,7 @@ def test_tc_matches_ffma_and_fp64(cuda_lib, m_in, m_out, cin, cout, K):
     outs, parts = {}, {}
     old = ops.SPCONV_IMPL
     try:
-        for impl in ("ffma", "tf32x3", "tf32"):
+        for impl in ("ffma", "tf32x3", "tf32", "hl"):
             ops.SPCONV_IMPL = impl
             y, part = ops.spconv(xc, cin, nc, Wc, cout, bias=bc, m_out=m_out, want_stats=True)
             torch.cuda.synchronize()
@@ -58,8 +59,10 @@ def test_tc_matches_ffma_and_fp64(cuda_lib, m_in, m_out, cin, cout, K):
     assert rel(outs["ffma"], want) < 2e-6
     assert rel(outs["tf32x3"], want) < 3e-5, rel(outs["tf32x3"], want)      # fp32-grade (2^-21 split residue)
     assert rel(outs["tf32"], want) < 3e-3, rel(outs["tf32"], want)          # single-pass tf32
+    if K > 1:
+        assert rel(outs["hl"], want) < 3e-5, rel(outs["hl"], want)          # half-pair operands: 22 significant bits, like 3xTF32
     # fused BatchNorm statistics agree with the column sums of the output
-    for impl in ("ffma", "tf32x3"):
+    for impl in ("ffma", "tf32x3", "hl"):
         s = parts[impl][:, 0].sum(0)
         q = parts[impl][:, 1].sum(0)
         assert torch.allclose(s, outs[impl].sum(0), rtol=1e-4, atol=1e-3), impl
