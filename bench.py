@@ -219,7 +219,7 @@ def cpu_sample(steps, warmup, max_level=2, workload="fragment"):
     for it in range(warmup + steps):
         f = it % stream_len
         if f not in frags:
-            frags[f] = synth.make_fragment(seed=1, frag_index=f, **fkw)
+            frags[f] = synth.make_fragment(seed=1, frag_index=synth.STREAM_FRAGMENTS[f] if stream_len > 1 else f, **fkw)
         inputs, fa, fb = frags[f]
         if f == 0:
             state = restate.FusionState()
@@ -367,7 +367,7 @@ def run_ours(args):
     # distinct input fragments: 1 (every rank / stream: its own copy of the same-shape fragment, weak scaling) or the 16 of a scene stream
     hosts = []
     for f in range(stream_len):
-        inputs, fa, fb = synth.make_fragment(seed=1, frag_index=f, **fkw)
+        inputs, fa, fb = synth.make_fragment(seed=1, frag_index=synth.STREAM_FRAGMENTS[f] if stream_len > 1 else f, **fkw)
         hosts.append(PackedHost({"inputs": {k: v for k, v in inputs.items() if torch.is_tensor(v) or isinstance(v, list) and torch.is_tensor(v[0])},
                                  "fa": fa, "fb": fb}))
         if f == 0:

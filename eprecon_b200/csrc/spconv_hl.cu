@@ -567,13 +567,26 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
         if (row < m_out) {
-          for (int z = 0; z < splits; ++z) {
-            const float4* src = reinterpret_cast<const float4*>(partial + ((size_t)z * m_out + row) * npad + col0 + cb);
+          // 4 splits = 16 independent 16-byte loads in flight per thread, then accumulate in ascending z (a plain z loop made
+          // this a chain of `splits` L2 round trips per column block: 107 us per 87-row conv instead of 43)
+          const size_t zstride = (size_t)m_out * npad;
+          const float* src0 = partial + (size_t)row * npad + col0 + cb;
+          for (int z0 = 0; z0 < splits; z0 += 4) {
+            float4 t4[4][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 t4 = __ldcg(src + i);
-              v[4 * i] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w;
-            }
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                t4[u][i] = (z0 + u < splits) ? __ldcg(reinterpret_cast<const float4*>(src0 + (size_t)(z0 + u) * zstride) + i)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (z0 + u < splits) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  v[4 * i] += t4[u][i].x; v[4 * i + 1] += t4[u][i].y; v[4 * i + 2] += t4[u][i].z; v[4 * i + 3] += t4[u][i].w;
+                }
+              }
           }
         }
       } else {
@@ -966,7 +979,13 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
   dim3 grid(ep_div_up(m_out, HTM), npad / nt, splits);
   const int bn_rows = ep_div_up(m_out, 64);
   const int tiles = (int)(grid.x * grid.y);
-  int32_t* ctr = (!use_tma && counters && counters_len >= 1 + tiles) ? counters : nullptr;
+  // The ticket path (last split of a tile reduces the partial sums in-kernel; last tile finalises the BatchNorm) is OFF by
+  // default: measured on B200 it is 2-4x SLOWER than the two small extra launches on exactly the problems it was meant for
+  // (87-640 rows: 185 vs 42 us) -- one CTA re-reading 27 split planes with a lane-per-row pattern (32 L1TEX wavefronts per
+  // load) and a single-CTA finalisation cannot compete with the wide, coalesced reduce / finalise kernels.
+  // EPRECON_HL_FUSE=1 enables it (profiles/r02_probe_small_conv_fused_vs_unfused.txt).
+  static const bool knob_fuse = [] { const char* v = getenv("EPRECON_HL_FUSE"); return v && v[0] == '1'; }();
+  int32_t* ctr = (knob_fuse && !use_tma && counters && counters_len >= 1 + tiles) ? counters : nullptr;
   // the finalisation runs on ONE CTA when fused: worth it while the partial-sum table is small (<= 1024 64-row tiles)
   const bool fuse_bn = ss_out && ctr && bn_rows <= 1024;
   if (use_tma) {
@@ -997,6 +1016,8 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
 
 // kernels ep_spconv_hl_fused_fwd launches for these arguments (1-3): conv [+ split-K reduce] [+ BatchNorm finalisation]
 int ep_spconv_hl_launches(int64_t m_out, int npad, int K, int have_counters, int want_ss) {
+  static const bool knob_fuse = [] { const char* v = getenv("EPRECON_HL_FUSE"); return v && v[0] == '1'; }();
+  if (!knob_fuse) have_counters = 0;
   const int nt = npad > 128 ? 128 : npad;
   const int splits = hl_splits(m_out, npad, K);
   const int bn_rows = ep_div_up(m_out, 64);
