@@ -346,6 +346,32 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
+// Input side: the reference hands the path a LIST of per-view NCHW maps (models/neuralrecon.py:53-54,
+// models/backbone.py:59-77) and stacks them (torch.stack, neucon_network.py:364).  This packs the V separately allocated maps
+// [bs, C, H, W] straight into the channels-last buffer [V, bs, H, W, C] the gather consumes: one launch instead of a stack
+// copy + a transpose, and each element moves once.
+struct ViewPtrs { const float* p[32]; };
+__global__ void __launch_bounds__(256) pack_views_nhwc_kernel(ViewPtrs views, float* __restrict__ out, int bs, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z;                 // v * bs + b
+  const int v = img / bs, b = img - v * bs;
+  const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = views.p[v] + (size_t)b * C * HW;
+  float* dst = out + (size_t)img * C * HW;
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    int c = c0 + ty + r, hw = hw0 + tx;
+    if (c < C && hw < HW) tile[ty + r][tx] = src[(size_t)c * HW + hw];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    int hw = hw0 + ty + r, c = c0 + tx;
+    if (c < C && hw < HW) dst[(size_t)hw * C + c] = tile[tx][ty + r];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Single-pass back-projection: projection + visibility + view count + stable compaction (decoupled
 // look-back over tiles) + bilinear gather in ONE kernel.  Sample positions computed in the visibility
@@ -683,6 +709,17 @@ int ep_backproject_grid(const int32_t* out_coords, const uint32_t* out_vis, int6
   bp_grid_kernel<<<ep_div_up(total, 256), 256, 0, stream>>>((const int4*)out_coords, out_vis, (int)m, n_views, bs,
                                                            (float)(feat_w - 1), (float)(feat_h - 1), origin,
                                                            voxel_size, krcam, im_grid, mask);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
+// views: host array of n_views device pointers, each a contiguous NCHW map [bs, channels, hw]; out [n_views, bs, hw, channels]
+int ep_pack_views_nhwc(const float* const* views, int n_views, int bs, int channels, int hw, float* out, cudaStream_t stream) {
+  if (!views || n_views < 1 || n_views > 32 || bs < 1 || channels < 1 || hw < 1) return EP_ERR_ARG;
+  ViewPtrs vp;
+  for (int v = 0; v < 32; ++v) vp.p[v] = v < n_views ? views[v] : nullptr;
+  dim3 grid(ep_div_up(hw, 32), ep_div_up(channels, 32), n_views * bs);
+  pack_views_nhwc_kernel<<<grid, 256, 0, stream>>>(vp, out, bs, channels, hw);
   EP_CHECK_LAUNCH();
   return EP_OK;
 }

@@ -354,7 +354,7 @@ Mat spconv(Exec& e, const float* x, int ldx, int m_in, const Conv& cv, const int
     }
     const size_t wsb = ep_spconv_hl_workspace_bytes(m_out, cv.npad, cv.K);
     void* ws = wsb ? (void*)alloc<char>(e, wsb) : nullptr;
-    RUN(e, ep_spconv_hl_launches(m_out, cv.npad, cv.K, e.counters != nullptr, bn != nullptr),
+    RUN(e, ep_spconv_hl_launches(m_out, cv.cin, cv.npad, cv.K, e.counters != nullptr, bn != nullptr),
         ep_spconv_hl_fused_fwd(xs, m_in, cv.cin, nbr, cv.K, cv.w_hl, cv.npad, cv.cout, cv.bias, o.p, o.ld, m_out, pp, ws, wsb, 0,
                                e.counters, kCounters, bn ? bn->gamma : nullptr, bn ? bn->beta : nullptr, bn ? bn->eps : 0.f, ssp,
                                e.st));

@@ -861,12 +861,19 @@ inline int pow2_cols(int n) {
   return c;
 }
 
-int hl_splits(int64_t m_out, int npad, int K) {
+// split-K over the kernel offsets for sub-wave problems.  nslab > 0 additionally keeps >= ~8 pipeline stages per CTA: a CTA
+// pays ~6 us of prologue + epilogue and writes a full fp32 partial tile, so 27 splits of 4 stages each (1-tile problems) spent
+// more time on partial sums than on the convolution; nslab == 0 gives the upper bound the workspace query needs.
+int hl_splits(int64_t m_out, int npad, int K, int nslab = 0) {
   const int nt = npad > 128 ? 128 : npad;
   const long long ctas = (long long)ep_div_up(m_out, HTM) * (npad / nt);
   if (K < 2 || ctas * 2 > EP_NUM_SMS) return 1;
   long long s = EP_NUM_SMS / ctas;
   if (s > K) s = K;
+  if (nslab > 0) {
+    const long long by_stages = ((long long)K * nslab) / 8;
+    if (s > by_stages) s = by_stages;
+  }
   return s < 2 ? 1 : (int)s;
 }
 
@@ -973,8 +980,8 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
     return e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
   }();
   if (attr != cudaSuccess) { g_hl_debug = 3; return EP_ERR_CUDA; }
-  const int splits = hl_splits(m_out, npad, K);
-  if (splits > 1 && workspace_bytes < ep_spconv_hl_workspace_bytes(m_out, npad, K)) return EP_ERR_WORKSPACE;
+  const int splits = hl_splits(m_out, npad, K, nslab);
+  if (splits > 1 && workspace_bytes < (size_t)splits * (size_t)m_out * (size_t)npad * sizeof(float)) return EP_ERR_WORKSPACE;
   float* partial = splits > 1 ? (float*)workspace : nullptr;
   dim3 grid(ep_div_up(m_out, HTM), npad / nt, splits);
   const int bn_rows = ep_div_up(m_out, 64);
@@ -1015,11 +1022,11 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
 }
 
 // kernels ep_spconv_hl_fused_fwd launches for these arguments (1-3): conv [+ split-K reduce] [+ BatchNorm finalisation]
-int ep_spconv_hl_launches(int64_t m_out, int npad, int K, int have_counters, int want_ss) {
+int ep_spconv_hl_launches(int64_t m_out, int cin, int npad, int K, int have_counters, int want_ss) {
   static const bool knob_fuse = [] { const char* v = getenv("EPRECON_HL_FUSE"); return v && v[0] == '1'; }();
   if (!knob_fuse) have_counters = 0;
   const int nt = npad > 128 ? 128 : npad;
-  const int splits = hl_splits(m_out, npad, K);
+  const int splits = hl_splits(m_out, npad, K, (cin + 31) / 32);
   const int bn_rows = ep_div_up(m_out, 64);
   const int tiles = ep_div_up(m_out, HTM) * (npad / nt);
   (void)tiles;

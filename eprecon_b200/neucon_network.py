@@ -182,11 +182,13 @@ class NeuConNet(nn.Module):
             else:
                 up_coords = ops.upsample8(pre_coords, interval)
                 min_view_number = 0
-            feats = torch.stack([feat[scale] for feat in features_backbone2d_occ_pano])
+            # the V per-view maps of this pyramid level go straight into the channels-last gather buffer (one launch; zero-copy
+            # when the caller hands channels-last storage) -- the reference stacks them (neucon_network.py:364)
+            feats_nhwc = ops.pack_views_nhwc([feat[scale] for feat in features_backbone2d_occ_pano])
             KRcam = inputs["proj_matrices"][:, :, scale].permute(1, 0, 2, 3).contiguous().float()
-            c_img = feats.shape[2]
+            c_img = feats_nhwc.shape[4]
             c_cat = c_img + pre_c
-            res = ops.backproject(up_coords, origin, cfg.VOXEL_SIZE, ops.to_nhwc(feats.float()), KRcam, min_view_number,
+            res = ops.backproject(up_coords, origin, cfg.VOXEL_SIZE, feats_nhwc, KRcam, min_view_number,
                                   mode="mean", want_src=True, alloc_width=ops.ceil4(c_cat))
             if res is None:
                 loss_dict[f"tsdf_occ_loss_{i}"] = self._zero_loss(origin)

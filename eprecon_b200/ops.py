@@ -75,6 +75,27 @@ def to_nhwc(feats):
     return out
 
 
+def pack_views_nhwc(views):
+    """Per-view feature maps -> ONE channels-last buffer [V,bs,H,W,C] (the layout the gather kernels consume).
+    `views`: list of V tensors [bs,C,H,W] (the reference's per-view backbone outputs, neuralrecon.py:53-54) -> one
+    ep_pack_views_nhwc launch (no torch.stack copy, no separate transpose); or a single tensor [V,bs,C,H,W] / an already
+    channels-last [V,bs,H,W,C]-strided one -> to_nhwc (zero-copy when the caller stores channels-last)."""
+    import ctypes
+    if torch.is_tensor(views):
+        return to_nhwc(views.float())
+    v0 = views[0]
+    bs, C, H, W = v0.shape
+    if not all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (bs, C, H, W) for t in views):
+        return to_nhwc(torch.stack([t.float() for t in views]))
+    V = len(views)
+    if V > 32:
+        return to_nhwc(torch.stack(list(views)))
+    out = torch.empty((V, bs, H, W, C), dtype=torch.float32, device=v0.device)
+    ptrs = (ctypes.c_void_p * V)(*[t.data_ptr() for t in views])
+    _lib.check(_lib.lib().ep_pack_views_nhwc(ptrs, V, bs, C, H * W, out.data_ptr(), stream_ptr()), "ep_pack_views_nhwc")
+    return out
+
+
 def backproject(coords, origin, voxel_size, feats_nhwc, krcam, min_views, mode="mean", out=None, out_col=0,
                 want_src=False, want_zbar=False, min_valid=1, alloc_width=None):
     """Project + visibility + stable compaction + bilinear gather.

@@ -60,6 +60,9 @@ int ep_backproject_grid(const int32_t* out_coords, const uint32_t* out_vis, int6
                         int feat_h, int feat_w, const float* origin, float voxel_size, const float* krcam,
                         float* im_grid, uint8_t* mask, cudaStream_t stream);
 int ep_nchw_to_nhwc(const float* in, float* out, int n_img, int channels, int hw, cudaStream_t stream);
+/* input side (models/neuralrecon.py:53-54, neucon_network.py:364): V separately allocated per-view NCHW maps [bs,C,hw] (host
+ * array of device pointers) -> one channels-last buffer [V,bs,hw,C]; replaces torch.stack + ep_nchw_to_nhwc */
+int ep_pack_views_nhwc(const float* const* views, int n_views, int bs, int channels, int hw, float* out, cudaStream_t stream);
 
 /* ---- scan / compaction / sort plumbing ----------------------------------------------------------------------
  * replaces torch.nonzero / boolean indexing / torch.unique (models/neucon_network.py:304,312,492-501;
@@ -134,7 +137,7 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
                            int cout, const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, void* workspace,
                            size_t workspace_bytes, int neg_row_mode, int32_t* counters, int counters_len, const float* gamma,
                            const float* beta, float eps, float* ss_out, cudaStream_t stream);
-int ep_spconv_hl_launches(int64_t m_out, int npad, int K, int have_counters, int want_ss);
+int ep_spconv_hl_launches(int64_t m_out, int cin, int npad, int K, int have_counters, int want_ss);
 int ep_hl_set_timeline(void* dev_buffer);   /* debug: clock64 timeline of one CTA of every following ep_spconv_hl launch */
 int ep_hl_debug_code(void);   /* last failure site of ep_spconv_hl_fwd: 1 map A, 2 map B, 3 smem attribute, 4 launch */
 int ep_hl_probe_gather4(const uint16_t* in_hl, int64_t m_in, int nslab, const int32_t* rows128, int slab, void* out16k,
