@@ -93,6 +93,12 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
   }
 }
 
+__device__ __forceinline__ long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return (long long)t;
+}
+
 __global__ void __launch_bounds__(H_THREADS)
 spconv_hl_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const int* __restrict__ nbr, int K, int nslab, int npad, int nt, int tmem_cols, int nstage, int cout,
@@ -371,7 +377,7 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
   const int row0 = blockIdx.x * HTM;
   const int col0 = blockIdx.y * nt;
   const int kb = (int)(((long long)blockIdx.z * K) / splits), ke = (int)(((long long)(blockIdx.z + 1) * K) / splits);
-  if (dbg && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) dbg[6 * 64 + 2] = clock64();
+  if (dbg && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) { dbg[6 * 64 + 2] = clock64(); dbg[394] = gtime_ns(); }
 
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
@@ -558,40 +564,93 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
       do_final = s_mask != 0;
       from_partial = true;
       if (do_final) __threadfence();
+      if (dbg && do_final && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) { dbg[390] = gtime_ns(); dbg[389] = blockIdx.z; }
     }
   }
-  if (do_final) {
-    for (int cb = cbeg; cb < cend; cb += 16) {
-      float v[16];
-      if (from_partial) {
+  if (do_final && from_partial) {
+    // ---- last split of the tile: reduce the `splits` partial planes, coalesced -- a warp walks rows, its lanes the row's
+    //      float4 column quads (one 512-byte row per load instruction; the first version mapped a lane to a ROW: 32 L1TEX
+    //      wavefronts per load, 50-120 us per tile).  Fixed order: z ascending per element, rows ascending per warp, warps
+    //      0..7 for the column statistics -> deterministic regardless of which CTA won the ticket.
+    const int nq = nt >> 2;
+    const size_t zstride = (size_t)m_out * npad;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (lane < nq && bias) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        if (row < m_out) {
-          // 4 splits = 16 independent 16-byte loads in flight per thread, then accumulate in ascending z (a plain z loop made
-          // this a chain of `splits` L2 round trips per column block: 107 us per 87-row conv instead of 43)
-          const size_t zstride = (size_t)m_out * npad;
-          const float* src0 = partial + (size_t)row * npad + col0 + cb;
-          for (int z0 = 0; z0 < splits; z0 += 4) {
-            float4 t4[4][4];
+      for (int j = 0; j < 4; ++j) bv[j] = (col0 + 4 * lane + j < cout) ? bias[col0 + 4 * lane + j] : 0.f;
+    }
+    for (int r = warp; r < HTM; r += 2 * (CP_THREADS / 32)) {
+      // two rows per trip: 2 x 8 independent 16-byte loads in flight per lane
+      const int rowa = row0 + r, rowb = rowa + CP_THREADS / 32;
+      if (rowa >= m_out) break;
+      const bool hasb = rowb < m_out && r + CP_THREADS / 32 < HTM;
+      if (lane < nq) {
+        const float* srca = partial + (size_t)rowa * npad + col0 + 4 * lane;
+        const float* srcb = partial + (size_t)rowb * npad + col0 + 4 * lane;
+        float4 acca = make_float4(0.f, 0.f, 0.f, 0.f), accb = acca;
+        for (int z0 = 0; z0 < splits; z0 += 8) {
+          float4 ta[8], tb[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 8; ++u) {
+            const bool on = z0 + u < splits;
+            ta[u] = on ? __ldcg(reinterpret_cast<const float4*>(srca + (size_t)(z0 + u) * zstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tb[u] = (on && hasb) ? __ldcg(reinterpret_cast<const float4*>(srcb + (size_t)(z0 + u) * zstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                t4[u][i] = (z0 + u < splits) ? __ldcg(reinterpret_cast<const float4*>(src0 + (size_t)(z0 + u) * zstride) + i)
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (z0 + u < splits) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  v[4 * i] += t4[u][i].x; v[4 * i + 1] += t4[u][i].y; v[4 * i + 2] += t4[u][i].z; v[4 * i + 3] += t4[u][i].w;
-                }
-              }
+          for (int u = 0; u < 8; ++u) {
+            if (z0 + u < splits) {
+              acca.x += ta[u].x; acca.y += ta[u].y; acca.z += ta[u].z; acca.w += ta[u].w;
+              accb.x += tb[u].x; accb.y += tb[u].y; accb.z += tb[u].z; accb.w += tb[u].w;
+            }
           }
         }
-      } else {
-        load_acc(cb, v);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !hasb) break;
+          const float4 acc = h == 0 ? acca : accb;
+          const int row_h = h == 0 ? rowa : rowb;
+          const float vals[4] = {acc.x + bv[0], acc.y + bv[1], acc.z + bv[2], acc.w + bv[3]};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = col0 + 4 * lane + j;
+            if (col < cout) {
+              out[(size_t)row_h * ld_out + col] = vals[j];
+              cs[j] += vals[j];
+              cq[j] += vals[j] * vals[j];
+            }
+          }
+        }
       }
+    }
+    if (bn_partial) {
+      float* red = reinterpret_cast<float*>(smem);     // [8 warps][2][128]; the operand ring is idle by now
+      if (lane < nq) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          red[(warp * 2 + 0) * 128 + 4 * lane + j] = cs[j];
+          red[(warp * 2 + 1) * 128 + 4 * lane + j] = cq[j];
+        }
+      }
+      __syncthreads();
+      if (tid < nt && col0 + tid < cout) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < CP_THREADS / 32; ++w) { s1 += red[(w * 2 + 0) * 128 + tid]; s2 += red[(w * 2 + 1) * 128 + tid]; }
+        const int col = col0 + tid;
+        const int r0 = 2 * blockIdx.x;   // bn_partial is sized for 64-row tiles: fill entry 2*bx, zero 2*bx+1
+        __stcg(&bn_partial[((size_t)r0 * 2 + 0) * cout + col], s1);
+        __stcg(&bn_partial[((size_t)r0 * 2 + 1) * cout + col], s2);
+        if (r0 + 1 < bn_rows) {
+          __stcg(&bn_partial[((size_t)(r0 + 1) * 2 + 0) * cout + col], 0.f);
+          __stcg(&bn_partial[((size_t)(r0 + 1) * 2 + 1) * cout + col], 0.f);
+        }
+      }
+    }
+  } else if (do_final) {
+    for (int cb = cbeg; cb < cend; cb += 16) {
+      float v[16];
+      load_acc(cb, v);
       float s[16], sq[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -618,9 +677,10 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
       }
     }
   }
+  if (dbg && do_final && from_partial && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) dbg[391] = gtime_ns();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (bn_partial && do_final && tid < nt) {
+  if (bn_partial && do_final && !from_partial && tid < nt) {
     const int col = col0 + tid;
     if (col < cout) {
       const float s = (s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid]);
@@ -646,6 +706,7 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
       if (old == total_tiles - 1) *counters = 0;
     }
     __syncthreads();
+    if (dbg && s_mask && tid == 0) dbg[392] = gtime_ns();
     if (s_mask) {
       __threadfence();
       double* s_s = reinterpret_cast<double*>(smem);          // [32][33]; the operand ring is idle by now
@@ -682,9 +743,10 @@ spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ C
         }
         __syncthreads();
       }
+      if (dbg && tid == 0) dbg[393] = gtime_ns();
     }
   }
-  if (dbg && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) dbg[6 * 64 + 1] = clock64();
+  if (dbg && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) { dbg[6 * 64 + 1] = clock64(); dbg[395] = gtime_ns(); }
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols));
   }

@@ -24,7 +24,7 @@ for cin, cout in ((24, 24), (74, 8), (96, 96)):
     w_hl, npad = ops._hl_weights(Wc, cout)
     x_hl = ops.hl_split(xc, cin)
     o = torch.empty((m, ops.ceil4(cout)), dtype=torch.float32, device="cuda")
-    dbg = torch.zeros(6 * 64 + 3, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(400, dtype=torch.int64, device="cuda")
     for it in range(3):
         if it == 2:
             L.ep_hl_set_timeline(dbg.data_ptr())

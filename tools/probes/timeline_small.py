@@ -56,9 +56,10 @@ for n_side, cin, cout in ((5, 128, 128), (11, 96, 96), (11, 64, 64), (26, 96, 96
         fused()
     host = (time.perf_counter() - t0) / 200 * 1e6
     torch.cuda.synchronize()
-    dbg = torch.zeros(6 * 64 + 3, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(400, dtype=torch.int64, device="cuda")
     L.ep_hl_set_timeline(dbg.data_ptr()); fused(); torch.cuda.synchronize(); L.ep_hl_set_timeline(0)
     d = dbg.cpu().tolist(); t0_ = d[386]
     rows = [[v - t0_ if v else None for v in d[6 * t:6 * t + 6]] for t in range(64) if d[6 * t + 2]]
+    print("final-CTA stamps (clk since the sampled CTA's entry): z", d[389], "[ns since the sampled CTA's entry] sampled CTA done", d[395] - d[394], "ticket won", d[390] - d[394], "reduce done", d[391] - d[394], "bn ticket won", d[392] - d[394], "finalise done", d[393] - d[394])
     print(f"m {m} cin {cin} cout {cout}: fused {t_f:.1f} us, unfused(+reduce kernel) {t_u:.1f} us, host issue {host:.1f} us/call; "
           f"CTA timeline: first stage {rows[0] if rows else None} last {rows[-1] if rows else None} mainloop_done {d[384] - t0_} epilogue_done {d[385] - t0_}")
