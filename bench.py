@@ -618,7 +618,7 @@ def run_ours(args):
         except Exception:
             pass
         impl_name = ops.SPCONV_IMPL
-        kname = {"hl": "spconv_hl_kernel (TMA tile::gather4 of pre-split half-pair rows -> tcgen05.mma kind::f16, fp32 TMEM accumulators)",
+        kname = {"hl": "spconv_hl_cp_kernel (cp.async gather of pre-split half-pair rows into the swizzled UMMA layout -> tcgen05.mma kind::f16, fp32 TMEM accumulators)",
                  "tf32x3": "spconv_tc_kernel<3> (register gather -> tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators)",
                  "tf32": "spconv_tc_kernel<1> (gather -> tcgen05.mma kind::tf32)",
                  "ffma": "spconv_kernel (gather-GEMM, fp32 FFMA)"}[impl_name]

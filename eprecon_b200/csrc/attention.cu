@@ -11,6 +11,7 @@
 // fixed chunk order by a second tiny kernel: deterministic, no atomics.  HBM-bound: 2 x 192 B of K / V + Q bytes of
 // mask per key, read once.
 #include "common.cuh"
+#include "eprecon_b200.h"
 
 namespace {
 
@@ -23,8 +24,8 @@ struct Partial { float m, l, acc[AD]; };   // 32 bytes
 
 __global__ void __launch_bounds__(8 * AQ)
 masked_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld_kv,
-                        const uint8_t* __restrict__ blocked, int n_keys, int n_queries, int n_heads, float scale,
-                        int keys_per_cta, Partial* __restrict__ part) {
+                        const uint8_t* __restrict__ blocked, const int* __restrict__ row_unblocked, int n_keys, int n_queries,
+                        int n_heads, float scale, int keys_per_cta, Partial* __restrict__ part) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int E = n_heads * AD;
   float* s_k = reinterpret_cast<float*>(smem);                    // [ATK][E]
@@ -52,7 +53,9 @@ masked_attention_kernel(const float* __restrict__ q, const float* __restrict__ k
     }
     for (int e = t; e < n_queries * ATK; e += nthreads) {
       const int qq = e / ATK, j = e - qq * ATK;
-      s_m[j * AQ + qq] = (j < nt && blocked) ? blocked[(size_t)qq * n_keys + base + j] : (uint8_t)(j >= nt);
+      // row_unblocked[q] == 0: every key of query q is blocked -> the query attends everywhere (mask3dformer.py:392)
+      const bool use_mask = blocked && (!row_unblocked || row_unblocked[qq] != 0);
+      s_m[j * AQ + qq] = (j < nt && use_mask) ? blocked[(size_t)qq * n_keys + base + j] : (uint8_t)(j >= nt);
     }
     __syncthreads();
     if (active) {
@@ -146,6 +149,15 @@ size_t ep_masked_attention_workspace_bytes(int64_t n_keys, int n_heads) {
 int ep_masked_attention(const float* q, const float* k, const float* v, int ld_kv, const uint8_t* blocked, int64_t n_keys,
                         int n_queries, int n_heads, int head_dim, float scale, float* out, void* workspace,
                         size_t workspace_bytes, cudaStream_t stream) {
+  return ep_masked_attention_flagged(q, k, v, ld_kv, blocked, nullptr, n_keys, n_queries, n_heads, head_dim, scale, out, workspace,
+                                     workspace_bytes, stream);
+}
+
+// row_unblocked (optional, int32 [n_queries]): 0 = every key of that query is blocked in `blocked`, so the query ignores the
+// mask (what the reference does by rewriting the mask, mask3dformer.py:392); saves a pass over the [n_queries, n_keys] flags.
+int ep_masked_attention_flagged(const float* q, const float* k, const float* v, int ld_kv, const uint8_t* blocked,
+                                const int32_t* row_unblocked, int64_t n_keys, int n_queries, int n_heads, int head_dim, float scale,
+                                float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (n_keys <= 0 || n_keys > 0x7fffffffLL || n_queries < 1 || n_heads < 1 || ld_kv % 4 != 0 || ld_kv < n_heads * head_dim)
     return EP_ERR_ARG;
   if (head_dim != AD || n_queries > AQ || n_heads > 8 || (n_heads * AD) % 4 != 0) return EP_ERR_UNSUPPORTED;
@@ -157,8 +169,8 @@ int ep_masked_attention(const float* q, const float* k, const float* v, int ld_k
   const int E = n_heads * AD;
   const size_t smem = (size_t)2 * ATK * E * sizeof(float) + (size_t)ATK * AQ;
   Partial* part = (Partial*)workspace;
-  masked_attention_kernel<<<grid, n_heads * AQ, smem, stream>>>(q, k, v, ld_kv, blocked, (int)n_keys, n_queries, n_heads, scale,
-                                                              keys_per_cta, part);
+  masked_attention_kernel<<<grid, n_heads * AQ, smem, stream>>>(q, k, v, ld_kv, blocked, row_unblocked, (int)n_keys, n_queries, n_heads,
+                                                              scale, keys_per_cta, part);
   EP_CHECK_LAUNCH();
   attention_combine_kernel<<<1, n_heads * AQ, 0, stream>>>(part, grid, n_queries, n_heads, out);
   EP_CHECK_LAUNCH();

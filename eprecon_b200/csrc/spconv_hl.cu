@@ -353,15 +353,19 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <bool CA>
+// TICKET = false (default) compiles the in-kernel split-K reduce / BatchNorm finalisation out: with them the kernel needs 112
+// registers (2 CTAs / SM), without 79 (3 CTAs / SM, the configuration the producers were tuned for; forcing 80 through
+// __launch_bounds__ on the ticket variant spills).  tests/test_capi_cpu.py pins the register count of the default variant.
+template <bool CA, bool TICKET>
 __global__ void __launch_bounds__(CP_THREADS)
 spconv_hl_cp_kernel(const uint8_t* __restrict__ in_hl, const __grid_constant__ CUtensorMap tm_b,
                     const int* __restrict__ nbr, int K, int nslab, int npad, int nt, int tmem_cols, int nstage, int cout,
                     const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m_out,
                     float* __restrict__ bn_partial, int bn_rows, int splits, float* __restrict__ partial,
-                    int* __restrict__ counters /* zeroed tickets: [0] finished tiles, [1 + tile] finished splits; or null */,
+                    int* __restrict__ counters_arg /* zeroed tickets: [0] finished tiles, [1 + tile] finished splits; or null */,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float bn_eps, float* __restrict__ ss_out,
                     long long* __restrict__ dbg /* optional timeline of one CTA: [stage][6] clock64 stamps */) {
+  int* const counters = TICKET ? counters_arg : nullptr;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int b_stage = nt * 128;
@@ -1037,9 +1041,11 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
   const size_t smem = (size_t)nstage * stage_bytes + (size_t)K * NBS * sizeof(int) + 1024;
   static const cudaError_t attr = [] {
     cudaError_t e1 = cudaFuncSetAttribute(spconv_hl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    cudaError_t e2 = cudaFuncSetAttribute(spconv_hl_cp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    cudaError_t e3 = cudaFuncSetAttribute(spconv_hl_cp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    return e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    cudaError_t e2 = cudaFuncSetAttribute(spconv_hl_cp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaError_t e3 = cudaFuncSetAttribute(spconv_hl_cp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaError_t e4 = cudaFuncSetAttribute(spconv_hl_cp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaError_t e5 = cudaFuncSetAttribute(spconv_hl_cp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    return e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4 != cudaSuccess ? e4 : e5;
   }();
   if (attr != cudaSuccess) { g_hl_debug = 3; return EP_ERR_CUDA; }
   const int splits = hl_splits(m_out, npad, K, nslab);
@@ -1063,16 +1069,11 @@ int ep_spconv_hl_fused_fwd(const uint16_t* in_hl, int64_t m_in, int cin, const i
                                                         out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial);
   } else {
     static const bool knob_ca = [] { const char* v = getenv("EPRECON_HL_CA"); return v && v[0] == '1'; }();
-    if (knob_ca)
-      spconv_hl_cp_kernel<true><<<grid, CP_THREADS, smem, stream>>>(reinterpret_cast<const uint8_t*>(in_hl), tm_b, nbr, K, nslab, npad, nt,
-                                                                    tmem_cols, nstage, cout, bias, out, ld_out, (int)m_out, bn_partial,
-                                                                    bn_rows, splits, partial, ctr, gamma, beta, eps,
-                                                                    fuse_bn ? ss_out : nullptr, g_hl_timeline);
-    else
-      spconv_hl_cp_kernel<false><<<grid, CP_THREADS, smem, stream>>>(reinterpret_cast<const uint8_t*>(in_hl), tm_b, nbr, K, nslab, npad, nt,
-                                                                     tmem_cols, nstage, cout, bias, out, ld_out, (int)m_out, bn_partial,
-                                                                     bn_rows, splits, partial, ctr, gamma, beta, eps,
-                                                                     fuse_bn ? ss_out : nullptr, g_hl_timeline);
+    auto kern = knob_ca ? (ctr ? spconv_hl_cp_kernel<true, true> : spconv_hl_cp_kernel<true, false>)
+                        : (ctr ? spconv_hl_cp_kernel<false, true> : spconv_hl_cp_kernel<false, false>);
+    kern<<<grid, CP_THREADS, smem, stream>>>(reinterpret_cast<const uint8_t*>(in_hl), tm_b, nbr, K, nslab, npad, nt, tmem_cols, nstage,
+                                             cout, bias, out, ld_out, (int)m_out, bn_partial, bn_rows, splits, partial, ctr, gamma,
+                                             beta, eps, fuse_bn ? ss_out : nullptr, g_hl_timeline);
   }
   if (splits > 1 && !ctr) {
     const int st = ep_internal_splitk_reduce(partial, splits, (int)m_out, npad, cout, bias, out, ld_out, bn_partial, stream);

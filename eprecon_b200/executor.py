@@ -15,6 +15,9 @@ Descriptor layout (flat int64, read sequentially by csrc/executor.cu::Reader):
   GRU level   = cv, ci, 2 x [convz (conv, lin), convr (conv, lin), convq (conv, lin)], END
   Linear4x    = n_heads, n_heads x [C_in, C_out, use_residual, lin1, ln1, lin2, ln2, lin3], END
   init head   = d, norm0, 7 x (conv, ln) of the ELAN, 3 x (conv, ln), subm4 conv, norm4, END
+  decoder     = query_feat, query_embed, level_embed, gauss_B, decoder_norm (g, b), class_embed (w, b), mask_embed 3 x (w, b),
+                6 x [ca in_proj (w, b), ca out_proj (w, b), ca norm (g, b), sa in_proj (w, b), sa out_proj (w, b), sa norm
+                (g, b), ffn linear1 (w, b), linear2 (w, b), ffn norm (g, b)], END      (plain f32 pointers, csrc/decoder.cu)
   globals     = [k3 offsets stride 1, 2, 4; k2 offsets stride 1, 2; subm3 offsets]   (device int32 [K,3] tables)
 Set EPRECON_EXEC=0 to run the per-kernel Python programs instead.
 """
@@ -31,7 +34,7 @@ from .ops import ceil4
 ENABLED = os.environ.get("EPRECON_EXEC", "1") != "0"
 ARENA_MB = int(os.environ.get("EPRECON_ARENA_MB", "1024"))
 ARENA_MAX_MB = int(os.environ.get("EPRECON_ARENA_MAX_MB", "32768"))
-_END = {"spvcnn": 0x5350564E, "gru": 0x47525546, "lin4x": 0x4C345854, "init": 0x494E4954}
+_END = {"spvcnn": 0x5350564E, "gru": 0x47525546, "lin4x": 0x4C345854, "init": 0x494E4954, "decoder": 0x44454344}
 
 
 def enabled():
@@ -144,13 +147,52 @@ def _build_init(m):
     return b.finish("init")
 
 
+def decoder_supported(m):
+    """csrc/decoder.cu is compiled for the one configuration the reference instantiates (neucon_network.py:59-71)."""
+    return (m.num_layers == 6 and m.num_queries == 80 and m.num_heads == 8 and m.query_feat.weight.shape[1] == 48
+            and m.class_embed.weight.shape[0] == 21 and m.mask_embed.layers[0].weight.shape[0] == 192
+            and m.mask_embed.layers[2].weight.shape[0] == 48 and m.transformer_ffn_layers[0].linear1.weight.shape[0] == 192
+            and m.pos_enc.normalize and tuple(m.pos_enc.gauss_B.shape) == (3, 24))
+
+
+def _build_decoder(m):
+    b = _Builder()
+
+    def ptrs(*ts):
+        for t in ts:
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise _lib.EpreconError("decoder parameters must be contiguous float32")
+            b.keep.append(t)
+            b.v.append(t.data_ptr())
+    ptrs(m.query_feat.weight, m.query_embed.weight, m.level_embed.weight, m.pos_enc.gauss_B,
+         m.decoder_norm.weight, m.decoder_norm.bias, m.class_embed.weight, m.class_embed.bias)
+    for lin in m.mask_embed.layers:
+        ptrs(lin.weight, lin.bias)
+    for j in range(m.num_layers):
+        ca, sa = m.transformer_cross_attention_layers[j], m.transformer_self_attention_layers[j]
+        ff = m.transformer_ffn_layers[j]
+        ptrs(ca.multihead_attn.in_proj_weight, ca.multihead_attn.in_proj_bias, ca.multihead_attn.out_proj.weight,
+             ca.multihead_attn.out_proj.bias, ca.norm.weight, ca.norm.bias,
+             sa.self_attn.in_proj_weight, sa.self_attn.in_proj_bias, sa.self_attn.out_proj.weight, sa.self_attn.out_proj.bias,
+             sa.norm.weight, sa.norm.bias, ff.linear1.weight, ff.linear1.bias, ff.linear2.weight, ff.linear2.bias,
+             ff.norm.weight, ff.norm.bias)
+    return b.finish("decoder")
+
+
 def _params_of(obj):
     mods = obj if isinstance(obj, (tuple, list)) else (obj,)
     for m in mods:
         yield from m.parameters()
 
 
-def _desc(owner, key, obj, build):
+def _tensors_of(obj):
+    for m in (obj if isinstance(obj, (tuple, list)) else (obj,)):
+        yield from m.parameters()
+        yield from m.buffers()
+
+
+def _desc(owner, key, obj, build, tensors=_params_of):
     """Descriptor of `obj` (a module or a tuple of modules), cached on `owner` and rebuilt when a parameter tensor was
     moved (.to / .cuda) or modified in place (load_state_dict, optimizer step).  The Parameter objects themselves are
     looked up once: walking nn.Module trees on every call cost 3 ms per fragment."""
@@ -161,7 +203,7 @@ def _desc(owner, key, obj, build):
         tag = tuple((p.data_ptr(), p._version) for p in hit[0])
         if tag == hit[1]:
             return hit[4]
-    plist = list(_params_of(obj))
+    plist = list(tensors(obj))
     tag = tuple((p.data_ptr(), p._version) for p in plist)
     arr, keep = build(obj)
     cache[key] = (plist, tag, arr, keep, arr.ctypes.data)
@@ -266,3 +308,26 @@ def init_head(mod, var, coords, shape):
          (_desc(mod, "init", mod, _build_init), _globals(dev), var.data_ptr(), var.stride(0), coords.data_ptr(), m,
           int(shape[0]), int(shape[1]), int(shape[2]), occ.data_ptr()))
     return occ
+
+
+def decoder(mod, rows, xyz, mask_rows, index, extent, want_aux=True):
+    """MultiScaleMaskedTransformerDecoder.forward body (csrc/decoder.cu).  rows[l] f32 [N_l, ld] (48 channels); xyz[l] int64
+    [N_l,3]; mask_rows f32 [N_2, ld]; index[0], index[1] int64 (nearest level-2 row of every level-0 / level-1 voxel)
+    -> pred_logits [7,80,21] (prediction on query_feat + one per layer), pred_masks [80,N_2], aux_masks [6,80,N_2] | None."""
+    L = _lib.lib()
+    dev = mask_rows.device
+    n = [int(r.shape[0]) for r in rows]
+    logits = torch.empty((7, 80, 21), dtype=torch.float32, device=dev)
+    masks = torch.empty((80, n[2]), dtype=torch.float32, device=dev)
+    aux = torch.empty((6, 80, n[2]), dtype=torch.float32, device=dev) if want_aux else None
+    ws_bytes = int(L.ep_exec_decoder_workspace_bytes(n[0], n[1], n[2]))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(L.ep_exec_decoder(_desc(mod, "decoder", mod, _build_decoder, _tensors_of), rows[0].data_ptr(), rows[0].stride(0),
+                                 rows[1].data_ptr(), rows[1].stride(0), rows[2].data_ptr(), rows[2].stride(0),
+                                 xyz[0].data_ptr(), xyz[1].data_ptr(), xyz[2].data_ptr(), n[0], n[1], n[2],
+                                 mask_rows.data_ptr(), mask_rows.stride(0), index[0].data_ptr(), index[1].data_ptr(),
+                                 float(extent[0]), float(extent[1]), float(extent[2]), logits.data_ptr(), masks.data_ptr(),
+                                 aux.data_ptr() if want_aux else 0, ws.data_ptr(), ws_bytes, ops.stream_ptr()), "ep_exec_decoder")
+    if want_aux:
+        _lib.LAUNCHES["n"] += 4          # the full-level-2 mask passes of the aux predictions taken on levels 0 / 1
+    return logits, masks, aux

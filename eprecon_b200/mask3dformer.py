@@ -18,8 +18,11 @@ What changes underneath:
     three `.item()` syncs per query.
   * the masked cross-attention over the voxel keys (6.2 of the decoder's 10 ms on the library route: batched GEMMs with
     an inner dimension of 6) is one fused pass over the keys, `ep_masked_attention` (csrc/attention.cu).
-The remaining dense algebra (K/V projections [N,48]x[48,48], the 80 x 80 self-attention, FFN, prediction heads) is a
-handful of small fp32 GEMMs on cuBLAS/ATen -- library calls like the dense 2-D fusion convs.
+  * the whole forward (K/V projections with the position encoding folded in, cross- and self-attention, FFN, prediction
+    heads, attention masks) is ONE native call, `ep_exec_decoder` (csrc/decoder.cu, 44 launches + 4 when the aux
+    predictions are requested), instead of 419 launches issued from Python in round 1.  EPRECON_NATIVE_DECODER=0 keeps
+    the per-op formulation (fused cross-attention + cuBLAS/ATen for the small GEMMs) that the native call is tested
+    against (tests/test_zz_panoptic_decoder_gpu.py).
 CUDA tensors only: there is no CPU path.
 """
 import math
@@ -29,13 +32,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import executor, ops
 from ._lib import EpreconError
 
 
 # cross-attention over the voxel keys through the fused kernel (csrc/attention.cu); the ATen formulation remains for the
 # 80 x 80 self-attention and for decoder shapes the kernel does not cover (head_dim != 6)
 FUSED_ATTENTION = os.environ.get("EPRECON_FUSED_ATTENTION", "1") != "0"
+NATIVE_DECODER = os.environ.get("EPRECON_NATIVE_DECODER", "1") != "0"
 
 
 def _need_cuda(t, what):
@@ -216,6 +220,9 @@ class MultiScaleMaskedTransformerDecoder(nn.Module):
         self.level_embed = nn.Embedding(self.num_feature_levels, hidden_dim)
         self.class_embed = nn.Linear(hidden_dim, num_classes + 1)
         self.mask_embed = MLP(hidden_dim, hidden_dim * 4, mask_dim, 3)
+        # the reference always returns the six intermediate predictions; only training consumes them -- callers that read
+        # pred_logits / pred_masks alone (NeuConNet's inference path) clear this and save 4 passes over [80, N_2]
+        self.aux_outputs = True
 
     def forward_prediction_heads(self, output, mask_rows, index):
         """output [Q,E]; mask_rows [N2,E]; index int64 [N_l] (None = all level-2 voxels) -> class logits [Q,classes+1],
@@ -238,6 +245,17 @@ class MultiScaleMaskedTransformerDecoder(nn.Module):
         mask_rows = mask_features[0].t().contiguous()
         c4 = [torch.cat([torch.zeros_like(x[:, :1]), x], 1).to(torch.int32).contiguous() for x in xyz]
         index = [nearest_fine_index(c4[0], c4[2], 5), nearest_fine_index(c4[1], c4[2], 1), None]
+        if NATIVE_DECODER and min(r.shape[0] for r in rows) > 0:
+            if not executor.decoder_supported(self):
+                raise EpreconError("the native decoder is built for the reference configuration (48 channels, 8 heads, 80 "
+                                   "queries, 6 layers, FFN 192, 20 classes); set EPRECON_NATIVE_DECODER=0 for other shapes")
+            extent = [float(s) for s in (spitial_shape.reshape(-1)[:3].tolist() if torch.is_tensor(spitial_shape) else spitial_shape)]
+            logits, masks, aux = executor.decoder(self, rows, [x.to(torch.int64).contiguous() for x in xyz], mask_rows, index,
+                                                  extent, want_aux=self.aux_outputs)
+            out = {"pred_logits": logits[6:7], "pred_masks": masks.unsqueeze(0)}
+            if self.aux_outputs:
+                out["aux_outputs"] = [{"pred_logits": logits[j:j + 1], "pred_masks": aux[j:j + 1]} for j in range(6)]
+            return out
         src, keys = [], []
         for l in range(3):
             s = rows[l] + self.level_embed.weight[l].unsqueeze(0)

@@ -220,6 +220,22 @@ int ep_mc_vertices(const float* vol, int dx, int dy, int dz, float level, const 
 int ep_mc_faces(const float* vol, int dx, int dy, int dz, float level, const int32_t* cell_index, const int32_t* tri_offset,
                 int64_t n_cells, const int32_t* edge_pos, int32_t* faces, cudaStream_t stream);
 
+int ep_masked_attention_flagged(const float* q, const float* k, const float* v, int ld_kv, const uint8_t* blocked,
+                                const int32_t* row_unblocked, int64_t n_keys, int n_queries, int n_heads, int head_dim, float scale,
+                                float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- panoptic decoder body as one native call (csrc/decoder.cu): MultiScaleMaskedTransformerDecoder.forward
+ * (models/mask3dformer.py:337-445; layers :70-200; models/voxel_position_encoding.py:42-146) for the reference configuration
+ * (48 channels, 8 heads, 80 queries, 6 layers, feed-forward 192, 20 classes).  desc: int64 parameter pointers, layout in
+ * eprecon_b200/executor.py::_build_decoder.  pred_logits f32 [7][80][21] (prediction on query_feat + one per layer),
+ * pred_masks f32 [80][n2] (last layer), aux_masks f32 [6][80][n2] or NULL. */
+size_t ep_exec_decoder_workspace_bytes(int64_t n0, int64_t n1, int64_t n2);
+int ep_exec_decoder(const int64_t* desc, const float* rows0, int ld0, const float* rows1, int ld1, const float* rows2, int ld2,
+                    const int64_t* xyz0, const int64_t* xyz1, const int64_t* xyz2, int64_t n0, int64_t n1, int64_t n2,
+                    const float* mask_rows, int ld_mask, const int64_t* index0, const int64_t* index1, float ex, float ey,
+                    float ez, float* pred_logits, float* pred_masks, float* aux_masks, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream);
+
 /* ---- small index helpers used by the native executor --------------------------------------------------------
  * ep_csr_expand: segments of a (voxel id)-keyed sort -> dense per-voxel [s0, s1) ranges (s0/s1 pre-zeroed; the scatter
  * the reference gets from torchsparse spcount/spvoxelize, ops/torchsparse_utils.py:51-58).  ep_translate_index:

@@ -21,6 +21,23 @@ def test_library_exports_every_declared_symbol():
     assert len(re.findall(r"\bep_\w+\s*\(", hdr)) == len(protos)      # the parser saw every prototype
 
 
+def test_dominant_conv_kernel_keeps_three_ctas_per_sm():
+    """The default sparse-conv kernel (spconv_hl_cp_kernel<CA=false, TICKET=false>) is tuned for 3 resident CTAs of 256 threads
+    per SM, i.e. at most 85 registers per thread and no spills; a silent register growth once cost a third of the occupancy."""
+    import shutil
+    import subprocess
+    import __graft_entry__ as g
+    g.build()
+    from eprecon_b200 import _lib
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "--dump-resource-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    hits = re.findall(r"Function (\S*spconv_hl_cp_kernelILb0ELb0E\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert len(hits) == 1, out[:400]
+    assert int(hits[0][1]) <= 85 and int(hits[0][2]) == 0, hits
+
+
 def test_header_has_no_torch_types():
     from eprecon_b200 import _lib
     hdr = re.sub(r"/\*.*?\*/", " ", open(_lib.HEADER_PATH).read(), flags=re.S)   # prototypes only, comments stripped

@@ -75,6 +75,67 @@ def test_decoder_matches_reference_fixture(decoder, gold):
     assert seg.dtype == torch.int32 and (seg.cpu().numpy() != gold["post_seg"]).mean() <= 1e-3
 
 
+def _decoder_inputs(gold):
+    coords = [torch.from_numpy(gold[f"coords{l}"].astype(np.int64)).cuda() for l in range(3)]
+    feats = [torch.from_numpy(gold[f"feats{l}"]).cuda() for l in range(3)]
+    mf = torch.from_numpy(gold["mask_features"]).cuda()
+    dim = int(gold["dim"])
+    return ([f.unsqueeze(0).permute(0, 2, 1) for f in feats], [c.unsqueeze(0) for c in coords], mf.unsqueeze(0).permute(0, 2, 1),
+            (dim, dim, dim))
+
+
+def test_native_decoder_aux_masks_match_reference_fixture(decoder, gold):
+    """The six intermediate mask predictions of the one-call decoder (csrc/decoder.cu) against the abs-sums the UNMODIFIED
+    reference produced, and the final prediction without the aux outputs requested (the masks buffer is then not written)."""
+    from eprecon_b200 import mask3dformer
+    assert mask3dformer.NATIVE_DECODER
+    out = decoder(*_decoder_inputs(gold))
+    for j, a in enumerate(out["aux_outputs"]):
+        got = a["pred_masks"][0].abs().sum().item()
+        assert abs(got - float(gold["aux_masks_abssum"][j])) <= RTOL * float(gold["aux_masks_abssum"][j]), j
+    decoder.aux_outputs = False
+    try:
+        lean = decoder(*_decoder_inputs(gold))
+    finally:
+        decoder.aux_outputs = True
+    assert "aux_outputs" not in lean
+    assert torch.equal(lean["pred_masks"], out["pred_masks"]) and torch.equal(lean["pred_logits"], out["pred_logits"])
+
+
+def test_native_decoder_matches_per_op_formulation(decoder, gold, monkeypatch):
+    """One native call vs the per-op route (fused cross-attention + ATen linears / LayerNorm / softmax): every prediction,
+    incl. a case where every query sees either all keys blocked or none (rank-one mask features: the sign of a query's mask
+    logit is then the same for every voxel) -> the fully blocked ones attend everywhere (mask3dformer.py:392)."""
+    from eprecon_b200 import mask3dformer
+    args = list(_decoder_inputs(gold))
+    for variant in ("fixture", "blocked"):
+        if variant == "blocked":
+            g = torch.Generator().manual_seed(3)
+            scale = (0.5 + torch.rand(args[2].shape[2], generator=g)).cuda()
+            args[2] = (torch.ones_like(args[2]) * scale.view(1, 1, -1)).contiguous()
+        native = decoder(*args)
+        monkeypatch.setattr(mask3dformer, "NATIVE_DECODER", False)
+        per_op = decoder(*args)
+        monkeypatch.setattr(mask3dformer, "NATIVE_DECODER", True)
+        assert rel(native["pred_logits"], per_op["pred_logits"]) < RTOL, variant
+        assert rel(native["pred_masks"], per_op["pred_masks"]) < RTOL, variant
+        if variant == "blocked":
+            sign = per_op["aux_outputs"][0]["pred_masks"][0] < 0
+            assert bool((sign.all(1) | (~sign).all(1)).all()) and bool(sign.all(1).any()) and bool((~sign).all(1).any())
+        for j in range(6):
+            assert rel(native["aux_outputs"][j]["pred_logits"], per_op["aux_outputs"][j]["pred_logits"]) < RTOL, (variant, j)
+            assert rel(native["aux_outputs"][j]["pred_masks"], per_op["aux_outputs"][j]["pred_masks"]) < RTOL, (variant, j)
+
+
+def test_native_decoder_rejects_other_shapes(cuda_lib, gold):
+    from eprecon_b200._lib import EpreconError
+    from eprecon_b200.mask3dformer import MultiScaleMaskedTransformerDecoder
+    dec = MultiScaleMaskedTransformerDecoder(mask_classification=True, num_classes=20, hidden_dim=48, num_queries=80, nheads=8,
+                                             dim_feedforward=192, dec_layers=3, pre_norm=False, mask_dim=48).cuda()
+    with pytest.raises(EpreconError):
+        dec(*_decoder_inputs(gold))
+
+
 @pytest.mark.parametrize("case", [0, 1, 2, 3])
 def test_panoptic_inference_matches_reference(cuda_lib, gold, case):
     from eprecon_b200.mask3dformer import panoptic_inference

@@ -3,11 +3,16 @@
     python tools/ncu_summary.py gpurun_out/x.ncu-rep [--stalls] > profiles/rNN_x_ncu_summary.txt
 
 --stalls adds the top warp-stall sites of the first launch (SASS instruction, share of samples, dominant reason).
+--traffic-json OUT --algorithmic BYTES [--launch J] writes the DRAM traffic of launch J (default 0) as the small JSON
+bench.py reads for `roofline.traffic` (profiles/r02_spconv_hl_ncu_traffic.json).
 """
 import csv
 import io
+import json
 import subprocess
 import sys
+
+UNIT_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 METRICS = [
     ("gpu__time_duration.sum", "duration"),
@@ -55,6 +60,23 @@ def main():
                 except ValueError:
                     pass
                 print(f"    {label:16s} {v} {units[i]}")
+    if "--traffic-json" in sys.argv:
+        out = sys.argv[sys.argv.index("--traffic-json") + 1]
+        j = int(sys.argv[sys.argv.index("--launch") + 1]) if "--launch" in sys.argv else 0
+        alg = float(sys.argv[sys.argv.index("--algorithmic") + 1]) if "--algorithmic" in sys.argv else None
+        r = body[j]
+
+        def nbytes(metric):
+            i = hdr.index(metric)
+            return float(r[i]) * UNIT_BYTES[units[i]]
+        name = r[kn].replace("void ", "").replace("<unnamed>::", "")
+        i_d = hdr.index("gpu__time_duration.sum")
+        with open(out, "w") as f:
+            json.dump({"source": rep, "launch": f"launch {j}: {name[:name.index('(') if '(' in name else 60]}, grid {r[hdr.index('launch__grid_size')]}, "
+                                                 f"{r[i_d]} {units[i_d]} under ncu",
+                       "dram_bytes_read": nbytes("dram__bytes_read.sum"), "dram_bytes_write": nbytes("dram__bytes_write.sum"),
+                       "algorithmic_bytes": alg}, f, indent=1)
+            f.write("\n")
     if "--stalls" in sys.argv:
         src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--launch-skip", "0", "--launch-count", "1"]))))
         h = src[1]
