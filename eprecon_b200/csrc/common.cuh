@@ -103,6 +103,27 @@ __host__ __device__ __forceinline__ uint64_t ep_morton_key(int x, int y, int z, 
   return ((uint64_t)(uint16_t)b << 48) | (ep_spread3((uint32_t)(x + 32768)) << 2) | (ep_spread3((uint32_t)(y + 32768)) << 1) |
          ep_spread3((uint32_t)(z + 32768));
 }
+// Compact form for coordinates known to lie in [-2^(cb-1), 2^(cb-1)) and 0 <= b < 2^bb: cb bits per axis (offset 2^(cb-1)),
+// batch above -> 3 * cb + bb key bits, so the radix sort needs ceil((3 cb + bb) / 8) passes instead of 8.  The ORDER equals
+// ep_morton_key's on such coordinates: there the per-axis bits are [sign, 15 - cb copies of !sign, low cb - 1 bits], and the
+// repeated levels never decide a comparison that the sign level left open.
+__host__ __device__ __forceinline__ bool ep_morton_compact_ok(int x, int y, int z, int b, int cb, int bb) {
+  const int h = 1 << (cb - 1);
+  return x >= -h && x < h && y >= -h && y < h && z >= -h && z < h && b >= 0 && b < (1 << bb);
+}
+__host__ __device__ __forceinline__ uint64_t ep_morton_key_compact(int x, int y, int z, int b, int cb) {
+  const int h = 1 << (cb - 1);
+  return ((uint64_t)(uint32_t)b << (3 * cb)) | (ep_spread3((uint32_t)(x + h)) << 2) | (ep_spread3((uint32_t)(y + h)) << 1) |
+         ep_spread3((uint32_t)(z + h));
+}
+__host__ __device__ __forceinline__ void ep_morton_unkey_compact(uint64_t k, int cb, int& x, int& y, int& z, int& b) {
+  const int h = 1 << (cb - 1);
+  b = (int)(k >> (3 * cb));
+  const uint64_t m = k & ((1ULL << (3 * cb)) - 1);
+  x = (int)ep_compact3(m >> 2) - h;
+  y = (int)ep_compact3(m >> 1) - h;
+  z = (int)ep_compact3(m) - h;
+}
 __host__ __device__ __forceinline__ void ep_morton_unkey(uint64_t k, int& x, int& y, int& z, int& b) {
   b = (int)(k >> 48);
   const uint64_t m = k & 0x0000FFFFFFFFFFFFULL;

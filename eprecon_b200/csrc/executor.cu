@@ -16,6 +16,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -162,17 +163,29 @@ inline T* alloc(Exec& e, size_t n) {
     }                                                  \
   } while (0)
 
-inline int read_i32(Exec& e, const int32_t* dev) {
+// `flag` (optional): a second device word fetched in the same stream drain; *flag_out = its value
+inline int read_i32(Exec& e, const int32_t* dev, const int32_t* flag = nullptr, int* flag_out = nullptr) {
   if (e.err) return 1;
   if (cudaMemcpyAsync(e.pinned, dev, sizeof(int32_t), cudaMemcpyDeviceToHost, e.st) != cudaSuccess ||
+      (flag && cudaMemcpyAsync(e.pinned + 1, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, e.st) != cudaSuccess) ||
       cudaStreamSynchronize(e.st) != cudaSuccess) {
     e.err = EP_ERR_CUDA;
     return 1;
   }
   const int v = e.pinned[0];
+  if (flag_out) *flag_out = flag ? e.pinned[1] : 0;
   if (v < 0) { e.err = EP_ERR_CUDA; return 1; }
   return v;
 }
+
+// Z-order sort keys come in three widths (csrc/common.cuh): tier 0 = 8 coordinate bits per axis, batch 0 (24 bits, 3 radix
+// passes), tier 1 = 9 + 5 batch bits (32 bits, 4 passes), kWideKeys = the 64-bit form (8 passes).  Same row order in all of
+// them.  A point cloud that does not fit its tier raises a device flag, is redone one tier up, and the process starts there
+// from then on (sticky: fragments of one deployment share their extent).
+constexpr int kWideKeys = 2;
+constexpr int kTierCoordBits[2] = {8, 9};
+constexpr int kTierBatchBits[2] = {0, 5};
+std::atomic<int> g_key_tier{[] { const char* v = getenv("EPRECON_KEY_TIER"); return v && v[0] >= '0' && v[0] <= '2' ? v[0] - '0' : 0; }()};
 
 inline void zero_bytes(Exec& e, void* p, size_t bytes) {
   if (e.err || bytes == 0) return;
@@ -182,7 +195,7 @@ inline void zero_bytes(Exec& e, void* p, size_t bytes) {
 
 // ------------------------------------------------------------------------------------------------ sparse structures
 struct Table { uint64_t* keys; int32_t* vals; int64_t cap; };
-struct VoxelSet { int32_t* coords; int m; int stride; Table t; int32_t* k3; };
+struct VoxelSet { int32_t* coords; int m; int stride; Table t; int32_t* k3; int key_tier; };
 struct Csr { const int32_t* perm; const int32_t* s0; const int32_t* s1; int m; };
 struct Seg { uint64_t* ks; int32_t* perm; int32_t* s0; int32_t* s1; int32_t* soi; int S; };
 struct PointCloud { int n; float* scaled; Csr csr1; VoxelSet vox; int32_t* tap_idx[3]; float* tap_w[3]; };
@@ -203,12 +216,13 @@ Table make_table(Exec& e, const int32_t* coords, int m, int batch_first) {
 
 VoxelSet make_voxelset(Exec& e, int32_t* coords, int m, int stride) {
   VoxelSet v;
-  v.coords = coords; v.m = m; v.stride = stride; v.k3 = nullptr;
+  v.coords = coords; v.m = m; v.stride = stride; v.k3 = nullptr; v.key_tier = kWideKeys;
   v.t = make_table(e, coords, m, 0);
   return v;
 }
 
-Seg sort_segments(Exec& e, const uint64_t* keys, int n, int key_bits, uint64_t sentinel, bool want_soi, bool want_count) {
+Seg sort_segments(Exec& e, const uint64_t* keys, int n, int key_bits, uint64_t sentinel, bool want_soi, bool want_count,
+                  const int32_t* flag = nullptr, int* flag_out = nullptr) {
   Seg s;
   s.ks = alloc<uint64_t>(e, n);
   s.perm = alloc<int32_t>(e, n);
@@ -219,9 +233,10 @@ Seg sort_segments(Exec& e, const uint64_t* keys, int n, int key_bits, uint64_t s
   const size_t mark = e.off;
   const size_t wsb = ep_sort_segments_workspace_bytes(n);
   void* ws = alloc<char>(e, wsb);
-  RUN(e, 12, ep_sort_segments(keys, n, key_bits, sentinel, s.ks, s.perm, s.s0, s.s1, s.soi, nseg, ws, wsb, e.st));
+  // iota + (histogram, scan, one onesweep pass per 8 key bits) + head flags / counts + scan + segment ids
+  RUN(e, 6 + (key_bits + 7) / 8, ep_sort_segments(keys, n, key_bits, sentinel, s.ks, s.perm, s.s0, s.s1, s.soi, nseg, ws, wsb, e.st));
   if (!e.err) e.off = mark;  // the sort's workspace is dead once it is enqueued (later users are stream-ordered after it)
-  s.S = want_count ? read_i32(e, nseg) : -1;
+  s.S = want_count ? read_i32(e, nseg, flag, flag_out) : -1;
   return s;
 }
 
@@ -230,13 +245,33 @@ void build_pc(Exec& e, PointCloud& pc, const float* pts, int n, float vres, bool
   for (int i = 0; i < 3; ++i) { pc.tap_idx[i] = nullptr; pc.tap_w[i] = nullptr; }
   pc.scaled = alloc<float>(e, 4 * (size_t)n);
   uint64_t* keys = alloc<uint64_t>(e, n);
-  RUN(e, 1, ep_point_keys(pts, n, vres, spatial ? 1 : 0, pc.scaled, keys, e.st));
-  Seg s = sort_segments(e, keys, n, spatial ? 64 : 60, kU64Max, true, true);
+  int tier = spatial ? g_key_tier.load(std::memory_order_relaxed) : kWideKeys;
+  Seg s;
+  for (;;) {
+    const size_t mark = e.off;
+    if (tier == kWideKeys) {
+      RUN(e, 1, ep_point_keys(pts, n, vres, spatial ? 1 : 0, pc.scaled, keys, e.st));
+      s = sort_segments(e, keys, n, spatial ? 64 : 60, kU64Max, true, true);
+      break;
+    }
+    int32_t* viol = alloc<int32_t>(e, 1);
+    zero_bytes(e, viol, sizeof(int32_t));
+    const int cb = kTierCoordBits[tier], bb = kTierBatchBits[tier];
+    RUN(e, 1, ep_point_keys_compact(pts, n, vres, cb, bb, pc.scaled, keys, viol, e.st));
+    int violated = 0;
+    s = sort_segments(e, keys, n, 3 * cb + bb, kU64Max, true, true, viol, &violated);
+    if (e.err || !violated) break;
+    e.off = mark;                                  // redo one tier up; remember it for the calls to come
+    ++tier;
+    int seen = g_key_tier.load(std::memory_order_relaxed);
+    while (seen < tier && !g_key_tier.compare_exchange_weak(seen, tier, std::memory_order_relaxed)) {}
+  }
   const int m = s.S;
   pc.csr1 = Csr{s.perm, s.s0, s.s1, m};
   int32_t* vox = alloc<int32_t>(e, 4 * (size_t)m);
   RUN(e, 1, ep_segment_coords(pc.scaled, s.perm, s.s0, m, vox, e.st));
   pc.vox = make_voxelset(e, vox, m, 1);  // keys = sphash(voxel coords): equal to the sorted point keys in hash order
+  pc.vox.key_tier = tier;
 }
 
 int32_t* kmap_k3(Exec& e, VoxelSet& v, const Globals& G) {
@@ -250,12 +285,17 @@ int32_t* kmap_k3(Exec& e, VoxelSet& v, const Globals& G) {
 void downsample(Exec& e, VoxelSet& v, const Globals& G, VoxelSet& coarse, int32_t*& nbr_down, int32_t*& nbr_up) {
   const int step = 2 * v.stride;
   uint64_t* keys = alloc<uint64_t>(e, v.m);
-  RUN(e, 1, ep_down_keys(v.coords, v.m, step, keys, e.st));
-  Seg s = sort_segments(e, keys, v.m, 64, kU64Max, false, true);
+  const int tier = v.key_tier;                     // the fine set fits its tier, so do the coarse sites
+  const int cb = tier == kWideKeys ? 0 : kTierCoordBits[tier];
+  if (cb) RUN(e, 1, ep_down_keys_compact(v.coords, v.m, step, cb, keys, e.st));
+  else RUN(e, 1, ep_down_keys(v.coords, v.m, step, keys, e.st));
+  Seg s = sort_segments(e, keys, v.m, cb ? 3 * cb + kTierBatchBits[tier] : 64, kU64Max, false, true);
   const int mc = s.S;
   int32_t* cc = alloc<int32_t>(e, 4 * (size_t)mc);
-  RUN(e, 1, ep_down_unpack(s.ks, s.s0, mc, cc, e.st));
+  if (cb) RUN(e, 1, ep_down_unpack_compact(s.ks, s.s0, mc, cb, cc, e.st));
+  else RUN(e, 1, ep_down_unpack(s.ks, s.s0, mc, cc, e.st));
   coarse = make_voxelset(e, cc, mc, step);
+  coarse.key_tier = tier;
   nbr_down = alloc<int32_t>(e, 8 * (size_t)mc);
   RUN(e, 1, ep_kmap_build(cc, mc, 0, G.k2[stride_slot(v.stride)], 8, v.t.keys, v.t.vals, v.t.cap, 0, 0, 0, nbr_down, e.st));
   nbr_up = alloc<int32_t>(e, 8 * (size_t)v.m);
@@ -553,6 +593,14 @@ size_t ep_exec_launch_count(void) { return g_launches.load(std::memory_order_rel
 // Per-launch profiling of the sparse-conv family for the CALLING host thread (see ProfRec).  enable(1) starts recording,
 // collect() synchronises the recorded events and returns up to `cap` records: meta[i] = {K, cin, cout, m_in, m_out, pairs,
 // impl (0 FFMA linear, 1 3xTF32, 2 half-pair TMA)}, ms[i] = device time between the bracketing events; recording stops.
+// Z-order sort-key tier new point clouds start in (0 = 24-bit keys, 1 = 32-bit, 2 = 64-bit; raised automatically when a cloud
+// does not fit).  set < 0 only queries.  Returns the tier in force before the call.
+int ep_exec_key_tier(int set) {
+  const int old = g_key_tier.load(std::memory_order_relaxed);
+  if (set >= 0 && set <= kWideKeys) g_key_tier.store(set, std::memory_order_relaxed);
+  return old;
+}
+
 int ep_exec_profile_enable(int on) {
   if (on) {
     if (!tl_prof) tl_prof = new Prof();

@@ -56,8 +56,11 @@ __global__ void coord_keys_kernel(const int4* __restrict__ coords, int m, int ba
 }
 
 // initial_voxelize front end (ops/torchsparse_utils.py:16-19): new = [C.xyz / vres, b]; key = sphash(floor(new))
+// cb > 0: compact Morton keys (common.cuh) -- a point outside the compact range raises *violation and the caller redoes the
+// keys in a wider form.
 __global__ void point_keys_kernel(const float4* __restrict__ pts, int n, float vres, int spatial,
-                                  float4* __restrict__ pts_scaled, uint64_t* __restrict__ keys) {
+                                  float4* __restrict__ pts_scaled, uint64_t* __restrict__ keys, int cb, int bb,
+                                  int* __restrict__ violation) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     float4 p = pts[i];
@@ -66,7 +69,13 @@ __global__ void point_keys_kernel(const float4* __restrict__ pts, int n, float v
     const int x = (int)floorf(q.x), y = (int)floorf(q.y), z = (int)floorf(q.z), b = (int)floorf(q.w);
     // spatial != 0: Morton key -> voxels come out in Z-order (gather locality); identical grouping, only the internal
     // row order differs from the reference's ascending-hash order
-    keys[i] = spatial ? ep_morton_key(x, y, z, b) : ep_sphash(x, y, z, b);
+    if (cb > 0) {
+      const bool ok = ep_morton_compact_ok(x, y, z, b, cb, bb);
+      if (!ok) *violation = 1;
+      keys[i] = ok ? ep_morton_key_compact(x, y, z, b, cb) : 0ull;
+    } else {
+      keys[i] = spatial ? ep_morton_key(x, y, z, b) : ep_sphash(x, y, z, b);
+    }
   }
 }
 
@@ -109,7 +118,7 @@ __global__ void kmap_inverse_kernel(const int* __restrict__ nbr, int m_out, int 
 
 // torchsparse spdownsample for k == s (nn/functional/downsample.py): trunc(c / (s*ts)) * (s*ts), then a
 // packed (b,x,y,z) key whose ascending order equals torch.unique(dim=0) on [b,x,y,z] rows.
-__global__ void down_keys_kernel(const int4* __restrict__ coords, int m, int step, uint64_t* __restrict__ keys) {
+__global__ void down_keys_kernel(const int4* __restrict__ coords, int m, int step, uint64_t* __restrict__ keys, int cb) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) {
     int4 c = coords[i];
@@ -118,16 +127,17 @@ __global__ void down_keys_kernel(const int4* __restrict__ coords, int m, int ste
     int y = (int)truncf(__fdiv_rn((float)c.y, (float)step)) * step;
     int z = (int)truncf(__fdiv_rn((float)c.z, (float)step)) * step;
     // (the reference sorts the coarse sites by (b,x,y,z); the order is internal, Z-order keeps conv tiles compact)
-    keys[i] = ep_morton_key(x, y, z, c.w);
+    keys[i] = cb > 0 ? ep_morton_key_compact(x, y, z, c.w, cb) : ep_morton_key(x, y, z, c.w);
   }
 }
 
 __global__ void unpack_down_keys_kernel(const uint64_t* __restrict__ keys_sorted, const int* __restrict__ seg_start,
-                                        int m, int4* __restrict__ coords) {
+                                        int m, int4* __restrict__ coords, int cb) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < m) {
     int x, y, z, b;
-    ep_morton_unkey(keys_sorted[seg_start[s]], x, y, z, b);
+    if (cb > 0) ep_morton_unkey_compact(keys_sorted[seg_start[s]], cb, x, y, z, b);
+    else ep_morton_unkey(keys_sorted[seg_start[s]], x, y, z, b);
     coords[s] = make_int4(x, y, z, b);
   }
 }
@@ -222,7 +232,19 @@ int ep_point_keys(const float* pts, int64_t n, float vres, int spatial, float* p
                   cudaStream_t stream) {
   if (n <= 0) return EP_ERR_ARG;
   point_keys_kernel<<<ep_div_up(n, 256), 256, 0, stream>>>((const float4*)pts, (int)n, vres, spatial,
-                                                           (float4*)pts_scaled, keys);
+                                                           (float4*)pts_scaled, keys, 0, 0, nullptr);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
+// Compact Z-order keys (3 * coord_bits + batch_bits bits, see common.cuh): same grouping and row order as the spatial keys of
+// ep_point_keys for voxel coordinates in [-2^(coord_bits-1), 2^(coord_bits-1)) and batch ids below 2^batch_bits; any point
+// outside sets *violation (int32, zeroed by the caller) and the keys must be redone in a wider form.
+int ep_point_keys_compact(const float* pts, int64_t n, float vres, int coord_bits, int batch_bits, float* pts_scaled,
+                          uint64_t* keys, int32_t* violation, cudaStream_t stream) {
+  if (n <= 0 || coord_bits < 1 || coord_bits > 16 || batch_bits < 0 || 3 * coord_bits + batch_bits > 63 || !violation) return EP_ERR_ARG;
+  point_keys_kernel<<<ep_div_up(n, 256), 256, 0, stream>>>((const float4*)pts, (int)n, vres, 1, (float4*)pts_scaled, keys,
+                                                           coord_bits, batch_bits, violation);
   EP_CHECK_LAUNCH();
   return EP_OK;
 }
@@ -259,7 +281,24 @@ int ep_kmap_inverse(const int32_t* nbr, int64_t m_out, int K, int32_t* inv, cuda
 
 int ep_down_keys(const int32_t* coords, int64_t m, int step, uint64_t* keys, cudaStream_t stream) {
   if (m <= 0 || step < 1) return EP_ERR_ARG;
-  down_keys_kernel<<<ep_div_up(m, 256), 256, 0, stream>>>((const int4*)coords, (int)m, step, keys);
+  down_keys_kernel<<<ep_div_up(m, 256), 256, 0, stream>>>((const int4*)coords, (int)m, step, keys, 0);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
+// coarse-site keys / coordinates in the compact form; the fine coordinates must already be inside the compact range (coarse
+// sites are trunc(c / step) * step, never farther from the origin than c)
+int ep_down_keys_compact(const int32_t* coords, int64_t m, int step, int coord_bits, uint64_t* keys, cudaStream_t stream) {
+  if (m <= 0 || step < 1 || coord_bits < 1 || coord_bits > 16) return EP_ERR_ARG;
+  down_keys_kernel<<<ep_div_up(m, 256), 256, 0, stream>>>((const int4*)coords, (int)m, step, keys, coord_bits);
+  EP_CHECK_LAUNCH();
+  return EP_OK;
+}
+
+int ep_down_unpack_compact(const uint64_t* keys_sorted, const int32_t* seg_start, int64_t m, int coord_bits, int32_t* coords,
+                           cudaStream_t stream) {
+  if (m <= 0 || coord_bits < 1 || coord_bits > 16) return EP_ERR_ARG;
+  unpack_down_keys_kernel<<<ep_div_up(m, 256), 256, 0, stream>>>(keys_sorted, seg_start, (int)m, (int4*)coords, coord_bits);
   EP_CHECK_LAUNCH();
   return EP_OK;
 }
@@ -267,7 +306,7 @@ int ep_down_keys(const int32_t* coords, int64_t m, int step, uint64_t* keys, cud
 int ep_down_unpack(const uint64_t* keys_sorted, const int32_t* seg_start, int64_t m, int32_t* coords,
                    cudaStream_t stream) {
   if (m <= 0) return EP_ERR_ARG;
-  unpack_down_keys_kernel<<<ep_div_up(m, 256), 256, 0, stream>>>(keys_sorted, seg_start, (int)m, (int4*)coords);
+  unpack_down_keys_kernel<<<ep_div_up(m, 256), 256, 0, stream>>>(keys_sorted, seg_start, (int)m, (int4*)coords, 0);
   EP_CHECK_LAUNCH();
   return EP_OK;
 }

@@ -75,14 +75,28 @@ __global__ void iota_kernel(int* __restrict__ p, int n) {
   if (i < n) p[i] = i;
 }
 
-// sorted keys -> segment heads: head[i] = (i==0 || key[i] != key[i-1]) && key[i] != sentinel
-__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int n, uint64_t sentinel,
-                                  uint8_t* __restrict__ head) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    uint64_t k = keys[i];
-    head[i] = (k != sentinel) && (i == 0 || keys[i - 1] != k);
+// head flags + per-CTA head counts in one pass over the sorted keys (head_flags_kernel + flag_count_kernel)
+__global__ void __launch_bounds__(kScanThreads)
+head_count_kernel(const uint64_t* __restrict__ keys, int n, uint64_t sentinel, uint8_t* __restrict__ head,
+                  int* __restrict__ block_count) {
+  __shared__ int s_scan[33];
+  const int base = blockIdx.x * kTile + threadIdx.x * kItems;
+  int c = 0;
+  uint64_t prev = (base > 0 && base - 1 < n) ? keys[base - 1] : 0ull;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const int i = base + k;
+    if (i < n) {
+      const uint64_t key = keys[i];
+      const bool h = (key != sentinel) && (i == 0 || prev != key);
+      head[i] = h;
+      c += h;
+      prev = key;
+    }
   }
+  int total;
+  ep_block_excl_scan(c, s_scan, &total);
+  if (threadIdx.x == 0) block_count[blockIdx.x] = total;
 }
 
 // After compaction of head flags: seg_start[s] = sorted position of segment s's head (= out_index),
@@ -90,7 +104,7 @@ __global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int n, uint
 __global__ void __launch_bounds__(kScanThreads)
 segment_ids_kernel(const uint8_t* __restrict__ head, const uint64_t* __restrict__ keys, uint64_t sentinel,
                    const int* __restrict__ perm, int n, const int* __restrict__ block_offset,
-                   int* __restrict__ seg_of_item, int* __restrict__ seg_end) {
+                   int* __restrict__ seg_start, int* __restrict__ seg_of_item, int* __restrict__ seg_end) {
   __shared__ int s_scan[33];
   const int base = blockIdx.x * kTile + threadIdx.x * kItems;
   int f[kItems], c = 0;
@@ -104,6 +118,7 @@ segment_ids_kernel(const uint8_t* __restrict__ head, const uint64_t* __restrict_
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     if (base + k < n) {
+      if (f[k] && seg_start) seg_start[ex] = base + k;           // stable compaction of the heads (flag_scatter_kernel's job)
       ex += f[k];
       const uint64_t key = keys[base + k];
       const bool dropped = key == sentinel;
@@ -174,11 +189,9 @@ int ep_sort_segments(const uint64_t* keys, int64_t n, int key_bits, uint64_t sen
   if (cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys, keys_sorted, iota, perm, (int)n, 0, key_bits,
                                       stream) != cudaSuccess)
     return EP_ERR_CUDA;
-  head_flags_kernel<<<ep_div_up(n, 256), 256, 0, stream>>>(keys_sorted, (int)n, sentinel, head);
-  flag_count_kernel<<<nblk, kScanThreads, 0, stream>>>(head, (int)n, bc);
+  head_count_kernel<<<nblk, kScanThreads, 0, stream>>>(keys_sorted, (int)n, sentinel, head, bc);
   scan_blocks_kernel<<<1, 1024, 0, stream>>>(bc, bo, nblk, n_segments_dev);
-  flag_scatter_kernel<<<nblk, kScanThreads, 0, stream>>>(head, (int)n, bo, seg_start, nullptr);
-  segment_ids_kernel<<<nblk, kScanThreads, 0, stream>>>(head, keys_sorted, sentinel, perm, (int)n, bo, seg_of_item,
+  segment_ids_kernel<<<nblk, kScanThreads, 0, stream>>>(head, keys_sorted, sentinel, perm, (int)n, bo, seg_start, seg_of_item,
                                                         seg_end);
   EP_CHECK_LAUNCH();
   return EP_OK;

@@ -93,6 +93,12 @@ int ep_kmap_inverse(const int32_t* nbr, int64_t m_out, int K, int32_t* inv, cuda
 int ep_down_keys(const int32_t* coords, int64_t m, int step, uint64_t* keys, cudaStream_t stream);
 int ep_down_unpack(const uint64_t* keys_sorted, const int32_t* seg_start, int64_t m, int32_t* coords,
                    cudaStream_t stream);
+/* compact Z-order keys: fewer radix-sort passes, same row order (csrc/common.cuh); *violation != 0 -> redo with the wide form */
+int ep_point_keys_compact(const float* pts, int64_t n, float vres, int coord_bits, int batch_bits, float* pts_scaled,
+                          uint64_t* keys, int32_t* violation, cudaStream_t stream);
+int ep_down_keys_compact(const int32_t* coords, int64_t m, int step, int coord_bits, uint64_t* keys, cudaStream_t stream);
+int ep_down_unpack_compact(const uint64_t* keys_sorted, const int32_t* seg_start, int64_t m, int coord_bits, int32_t* coords,
+                           cudaStream_t stream);
 int ep_devox_prepare(const float* pts_scaled, int64_t n, int stride, const uint64_t* table_keys,
                      const int32_t* table_vals, int64_t capacity, int32_t* idx, float* weights, cudaStream_t stream);
 int ep_point_query(const float* pts_scaled, int64_t n, int stride, const uint64_t* table_keys,
@@ -260,6 +266,9 @@ int ep_exec_desc_check(int kind, const int64_t* desc);   /* host-only descriptor
 /* per-launch CUDA-event timing of the sparse-conv family inside the executor (calling host thread only): enable(1), run
  * fragments, collect() -> number of records; meta int64 [cap,7] = {K, cin, cout, m_in, m_out, valid pairs, impl}, ms [cap]. */
 int ep_exec_profile_enable(int on);
+/* width tier of the executor's Z-order sort keys (0: 24 bits, 1: 32 bits, 2: 64 bits; raised automatically, sticky);
+ * set < 0 only queries; returns the tier in force before the call */
+int ep_exec_key_tier(int set);
 int ep_exec_profile_collect(int64_t* meta, float* ms, int cap);
 int ep_exec_spvcnn(const int64_t* desc, const int64_t* globals, const float* pts, const float* feat, int ld_feat,
                    int64_t n, float vres, float* out, int ld_out, void* arena, size_t arena_bytes, int64_t* stats,

@@ -89,6 +89,38 @@ def test_executor_bit_identical_to_python_programs(cuda_lib, with_pano):
         _same(out_e2["tsdf"], out_p2["tsdf"], "tsdf2")
 
 
+@pytest.mark.parametrize("shift,batches,want_tier", [(0.0, 1, 0), (0.0, 2, 1), (8.0, 1, 1), (30.0, 1, 2)])
+def test_executor_sort_key_tiers_keep_the_row_order(cuda_lib, shift, batches, want_tier):
+    """The executor sorts voxels by compact Z-order keys (24 / 32 bits) when the cloud fits and falls back to wider keys
+    when it does not; every tier must give the rows in the order of the 64-bit keys the Python programs use -> the module
+    output is bit-identical whatever tier ends up in force."""
+    from eprecon_b200 import executor
+    from eprecon_b200.modules import SPVCNN
+    from eprecon_b200.tensor import PointTensor
+    torch.manual_seed(0)
+    net = SPVCNN(num_classes=1, in_channels=24, pres=1, cr=0.25, vres=0.04, dropout=False).cuda()
+    n = 20000
+    g = torch.Generator().manual_seed(4)
+    xyz = (torch.rand(n, 3, generator=g) - 0.5) * 4.0 + shift              # +-2 m = +-50 voxels around `shift` metres
+    b = torch.randint(0, batches, (n, 1), generator=g).float()
+    pts = torch.cat([xyz, b], 1).cuda()
+    feat = torch.randn(n, 24, generator=g).cuda()
+    old = executor.ENABLED
+    L = cuda_lib
+    L.ep_exec_key_tier(0)
+    try:
+        executor.ENABLED = True
+        got = net(PointTensor(feat, pts)).clone()
+        assert L.ep_exec_key_tier(-1) == want_tier
+        again = net(PointTensor(feat, pts)).clone()                        # starts in the raised tier: no retry
+        executor.ENABLED = False
+        want = net(PointTensor(feat, pts)).clone()
+    finally:
+        executor.ENABLED = old
+        L.ep_exec_key_tier(0)
+    assert torch.equal(got, want) and torch.equal(again, want)
+
+
 def test_executor_grows_its_arena(cuda_lib):
     """A scratch arena that is too small is reported (EP_ERR_WORKSPACE) and grown, never overrun."""
     from eprecon_b200 import executor
