@@ -2,8 +2,8 @@
 //
 // Replaces torchsparse v2.0.0 `spnn.Conv3d` forward (gather -> cuBLAS GEMM -> scatter-add per kernel
 // offset; reference call sites models/modules.py:19,35,50,56,64,90,181), spconv `SubMConv3d`
-// (models/modules.py:252,444) and, with K == 1 and no neighbour table, every dense per-row nn.Linear on
-// the path (models/modules.py:127-136,187,279-284).
+// (models/modules.py:252,444) and, with K == 1 and no neighbour table, the dense per-row nn.Linear layers of the path
+// (models/modules.py:127-136,187,279-284) whose weights are too wide for the tensor-core row kernel (csrc/linear_mma.cu).
 //
 //   out[j, :] = bias + sum_k  W[k]^T . in[nbr[j, k], :]        (rows with nbr < 0 contribute nothing)
 //
@@ -216,196 +216,10 @@ bn_finalize_kernel(const float* __restrict__ bn_partial, int nblk, int c, int m,
 }
 
 
-// ------------------------------------------------------------------------------------------------------------------
-// K == 1, no neighbour table: a dense per-row linear  out[r, :] = bias + in[r, :cin] W.  The gather-GEMM tile above spends
-// three shared-memory loads per eight FMAs on it (1.4-1.7 TB/s of row traffic on L2-resident rows); here every thread owns
-// two rows and NC output columns, so one 16-byte load of its row feeds 4 x NC FMAs and the weight rows are warp-wide
-// broadcasts: 8 + NC shared-memory wavefronts per 8 x NC FMAs.
-//   * CTA = 128 threads = LR_ROWS (256) rows = four 64-row BatchNorm tiles; persistent over row chunks (W staged once);
-//   * the rows stream through a two-stage cp.async ring of 16-channel slices, stored with a 16-byte XOR swizzle so that the
-//     per-thread float4 reads are conflict free;
-//   * cout > NC runs as several column passes over the (L1-resident) rows;
-//   * epilogue through shared memory: coalesced row stores + per-tile column sums in ascending row order (deterministic).
-// Same accumulation order per output element as spconv_kernel (ascending input channel, bias added last): bit-identical.
-constexpr int LR_ROWS = 256;
-constexpr int LR_THREADS = 128;
-constexpr int LR_KC = 16;                       // input channels per ring stage (64 bytes per row)
-
-__device__ __forceinline__ void lr_cp16(void* dst, const void* src, bool pred) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  const int bytes = pred ? 16 : 0;              // src-size 0: the 16 bytes are zero-filled
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
-}
-
-template <int NC>
-__global__ void __launch_bounds__(LR_THREADS)
-linear_rows_kernel(const float* __restrict__ in, int ld_in, int cin, const float* __restrict__ W, int ldw, int cout,
-                   const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m, float* __restrict__ bn_partial,
-                   int npass) {
-  extern __shared__ __align__(16) float lr_smem[];
-  // [2][LR_ROWS][LR_KC] ring, reused as the [LR_ROWS][NC + 1] output staging tile; then W as [cin4][npass * NC]
-  constexpr int RING = 2 * LR_ROWS * LR_KC;
-  constexpr int STAGE = LR_ROWS * (NC + 1);
-  constexpr int HEAD = RING > STAGE ? RING : STAGE;
-  float* s_a = lr_smem;
-  float* s_w = lr_smem + HEAD;
-  const int tid = threadIdx.x;
-  const int cin4 = (cin + 3) & ~3;
-  const int ws = npass * NC;
-  {
-    // weights: 16-byte asynchronous copies (all in flight at once; they land before the first stage is consumed), zeros in the
-    // padding rows / columns
-    const int wq = ws >> 2, lq = ldw >> 2;
-    for (int e = tid; e < cin4 * wq; e += LR_THREADS) {
-      const int i = e / wq, j = e - i * wq;
-      if (i < cin && j < lq) lr_cp16(s_w + i * ws + j * 4, W + (size_t)i * ldw + j * 4, true);
-      else *reinterpret_cast<float4*>(s_w + i * ws + j * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  const int nk = (cin4 + LR_KC - 1) / LR_KC;
-  const int nchunk = (m + LR_ROWS - 1) / LR_ROWS;
-  const int sw = (tid >> 1) & 3;                 // swizzle of rows tid and tid + 128 (same parity and (row >> 1) & 3)
-
-  for (int chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
-    const int row0 = chunk * LR_ROWS;
-    auto load_stage = [&](int ks, int buf) {
-      // LR_ROWS rows x 4 16-byte pieces; consecutive threads take consecutive pieces of a row
-      float* dst0 = s_a + buf * (LR_ROWS * LR_KC);
-#pragma unroll
-      for (int it = 0; it < LR_ROWS * 4 / LR_THREADS; ++it) {
-        const int e = it * LR_THREADS + tid;
-        const int r = e >> 2, c = e & 3;
-        const int ch = ks * LR_KC + c * 4;
-        const bool ok = row0 + r < m && ch < cin4;
-        const float* src = ok ? in + (size_t)(row0 + r) * ld_in + ch : in;
-        lr_cp16(dst0 + r * LR_KC + ((c ^ ((r >> 1) & 3)) << 2), src, ok);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    for (int pass = 0; pass < npass; ++pass) {
-      const int cb = pass * NC;
-      float acc0[NC], acc1[NC];
-#pragma unroll
-      for (int j = 0; j < NC; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-      __syncthreads();                            // the staging tile of the previous pass / chunk is drained; W is visible
-      load_stage(0, 0);
-      for (int ks = 0; ks < nk; ++ks) {
-        const int buf = ks & 1;
-        if (ks + 1 < nk) {
-          load_stage(ks + 1, buf ^ 1);
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        const float* a_base = s_a + buf * (LR_ROWS * LR_KC);
-        const int kmax = min(LR_KC, cin4 - ks * LR_KC) >> 2;
-        for (int i4 = 0; i4 < kmax; ++i4) {
-          const float4 a0 = *reinterpret_cast<const float4*>(a_base + tid * LR_KC + ((i4 ^ sw) << 2));
-          const float4 a1 = *reinterpret_cast<const float4*>(a_base + (tid + 128) * LR_KC + ((i4 ^ sw) << 2));
-          const float av0[4] = {a0.x, a0.y, a0.z, a0.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w};
-          const float* wrow = s_w + (size_t)(ks * LR_KC + i4 * 4) * ws + cb;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int j4 = 0; j4 < NC / 4; ++j4) {
-              const float4 w = *reinterpret_cast<const float4*>(wrow + u * ws + j4 * 4);
-              acc0[4 * j4 + 0] = fmaf(av0[u], w.x, acc0[4 * j4 + 0]); acc1[4 * j4 + 0] = fmaf(av1[u], w.x, acc1[4 * j4 + 0]);
-              acc0[4 * j4 + 1] = fmaf(av0[u], w.y, acc0[4 * j4 + 1]); acc1[4 * j4 + 1] = fmaf(av1[u], w.y, acc1[4 * j4 + 1]);
-              acc0[4 * j4 + 2] = fmaf(av0[u], w.z, acc0[4 * j4 + 2]); acc1[4 * j4 + 2] = fmaf(av1[u], w.z, acc1[4 * j4 + 2]);
-              acc0[4 * j4 + 3] = fmaf(av0[u], w.w, acc0[4 * j4 + 3]); acc1[4 * j4 + 3] = fmaf(av1[u], w.w, acc1[4 * j4 + 3]);
-            }
-          }
-        }
-        __syncthreads();                          // the buffer may be refilled (or become the staging tile)
-      }
-      // epilogue: bias, stage, coalesced store, per-tile column statistics
-      float* s_o = s_a;
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        const float bv = (bias && cb + j < cout) ? __ldg(bias + cb + j) : 0.f;
-        s_o[tid * (NC + 1) + j] = acc0[j] + bv;
-        s_o[(tid + 128) * (NC + 1) + j] = acc1[j] + bv;
-      }
-      __syncthreads();
-      const int ncol = min(NC, cout - cb);
-      if (ncol > 0) {
-        for (int e = tid; e < LR_ROWS * NC; e += LR_THREADS) {
-          const int r = e / NC, j = e - r * NC;
-          if (j < ncol && row0 + r < m) out[(size_t)(row0 + r) * ld_out + cb + j] = s_o[r * (NC + 1) + j];
-        }
-        if (bn_partial) {
-          for (int p = tid; p < 4 * NC; p += LR_THREADS) {
-            const int tile = p / NC, j = p - tile * NC;
-            const int tile_row0 = row0 + tile * 64;
-            if (j < ncol && tile_row0 < m) {
-              const int nr = min(64, m - tile_row0);
-              float sm = 0.f, sq = 0.f;
-              for (int r = 0; r < nr; ++r) {
-                const float v = s_o[(tile * 64 + r) * (NC + 1) + j];
-                sm += v;
-                sq = fmaf(v, v, sq);
-              }
-              const size_t t = (size_t)(tile_row0 >> 6);
-              bn_partial[(t * 2 + 0) * cout + cb + j] = sm;
-              bn_partial[(t * 2 + 1) * cout + cb + j] = sq;
-            }
-          }
-        }
-      }
-    }
-  }
-}
-
-template <int NC>
-int launch_linear_rows(const float* in, int ld_in, int cin, const float* W, int ldw, int cout, const float* bias, float* out,
-                       int ld_out, int64_t m, float* bn_partial, int npass, cudaStream_t stream) {
-  constexpr int RING = 2 * LR_ROWS * LR_KC, STAGE = LR_ROWS * (NC + 1);
-  const int cin4 = (cin + 3) & ~3;
-  const size_t smem = ((size_t)(RING > STAGE ? RING : STAGE) + (size_t)cin4 * npass * NC) * sizeof(float);
-  static const cudaError_t attr = cudaFuncSetAttribute(linear_rows_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  if (attr != cudaSuccess) return EP_ERR_CUDA;
-  const int nchunk = ep_div_up(m, LR_ROWS);
-  static const int sms = [] {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
-    return n;
-  }();
-  // persistent CTAs, c per SM: the c whose last round of row chunks is fullest (820 chunks on 148 x 4 CTAs would leave a
-  // third of the machine idle in round two)
-  int per_sm = (int)(200 * 1024 / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : per_sm > 4 ? 4 : per_sm;
-  int grid = nchunk;
-  if (nchunk > sms) {
-    double best = -1.0;
-    for (int c = 1; c <= per_sm; ++c) {
-      const int gsz = sms * c;
-      const int rounds = ep_div_up(nchunk, gsz);
-      const double eff = (double)nchunk / ((double)rounds * gsz) + 1e-3 * c;
-      if (eff > best) { best = eff; grid = gsz; }
-    }
-    if (grid > nchunk) grid = nchunk;
-  }
-  linear_rows_kernel<NC><<<grid, LR_THREADS, smem, stream>>>(in, ld_in, cin, W, ldw, cout, bias, out, ld_out, (int)m, bn_partial, npass);
-  return EP_OK;
-}
-
-// column-pass width and count for a dense linear; 0 = keep the gather-GEMM tile (weights too large for shared memory)
-inline int linear_rows_plan(int cin, int cout, int* npass) {
-  const int c4 = (cout + 3) & ~3;
-  int nc;
-  if (c4 <= 8) nc = 8;
-  else if (c4 <= 16) nc = 16;
-  else if (c4 <= 24) nc = 24;
-  else if (c4 <= 32) nc = 32;
-  else nc = (ep_div_up(c4, 24) * 24 < ep_div_up(c4, 32) * 32) ? 24 : 32;
-  *npass = ep_div_up(c4, nc);
-  const int cin4 = (cin + 3) & ~3;
-  const size_t smem = ((size_t)max(2 * LR_ROWS * LR_KC, LR_ROWS * (nc + 1)) + (size_t)cin4 * *npass * nc) * sizeof(float);
-  return smem <= 100 * 1024 ? nc : 0;
-}
-
 }  // namespace
+
+int ep_internal_linear_mma(const float* in, int ld_in, int cin, const float* W, int ldw, int cout, const float* bias, float* out,
+                           int ld_out, int64_t m, float* bn_partial, cudaStream_t stream);   // csrc/linear_mma.cu
 
 extern "C" {
 
@@ -417,15 +231,11 @@ int ep_spconv_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, int K
                   const float* bias, float* out, int ld_out, int64_t m_out, float* bn_partial, cudaStream_t stream) {
   if (m_out <= 0 || cin < 1 || cout < 1 || K < 1 || ld_in % 4 != 0 || ldw % 4 != 0 || ldw < cout) return EP_ERR_ARG;
   if (!nbr && K != 1) return EP_ERR_ARG;
-  static const bool knob_rows = [] { const char* v = getenv("EPRECON_LINEAR_ROWS"); return !(v && v[0] == '0'); }();
-  if (!nbr && knob_rows && in != out) {
-    int npass = 0;
-    const int nc = linear_rows_plan(cin, cout, &npass);
-    int st = EP_ERR_UNSUPPORTED;
-    if (nc == 8) st = launch_linear_rows<8>(in, ld_in, cin, W, ldw, cout, bias, out, ld_out, m_out, bn_partial, npass, stream);
-    else if (nc == 16) st = launch_linear_rows<16>(in, ld_in, cin, W, ldw, cout, bias, out, ld_out, m_out, bn_partial, npass, stream);
-    else if (nc == 24) st = launch_linear_rows<24>(in, ld_in, cin, W, ldw, cout, bias, out, ld_out, m_out, bn_partial, npass, stream);
-    else if (nc == 32) st = launch_linear_rows<32>(in, ld_in, cin, W, ldw, cout, bias, out, ld_out, m_out, bn_partial, npass, stream);
+  // dense linears run on the 3xTF32 row kernel (csrc/linear_mma.cu) unless their weights are too wide for it or
+  // EPRECON_LINEAR=tile asks for the fp32 FFMA tile kernel below
+  static const bool knob_tile = [] { const char* v = getenv("EPRECON_LINEAR"); return v && v[0] == 't'; }();
+  if (!nbr && !knob_tile && in != out) {
+    const int st = ep_internal_linear_mma(in, ld_in, cin, W, ldw, cout, bias, out, ld_out, m_out, bn_partial, stream);
     if (st != EP_ERR_UNSUPPORTED) {
       if (st != EP_OK) return st;
       EP_CHECK_LAUNCH();

@@ -1,7 +1,8 @@
-"""Dense per-row linear (ep_spconv_fwd with K == 1 and no neighbour table -> linear_rows_kernel, csrc/spconv.cu): the nn.Linear
-layers of the path (reference: models/modules.py:127-136,187,279-284).  Checked against
-  * an fp64 matmul of the same operands (fp32 tolerance),
-  * the gather-GEMM tile kernel fed an identity neighbour table -- same per-element accumulation order, so BIT-exact outputs,
+"""Dense per-row linear (ep_spconv_fwd with K == 1 and no neighbour table -> linear_mma_kernel, csrc/linear_mma.cu: 3xTF32 on
+the tensor cores, rows straight from global memory into MMA fragments): the nn.Linear layers of the path (reference:
+models/modules.py:127-136,187,279-284).  Checked against
+  * an fp64 matmul of the same operands: |err| <= 2e-6 * scale * sqrt(cin) -- fp32-class accuracy, the tolerance of the FFMA kernel,
+  * the fp32 FFMA gather-GEMM tile kernel fed an identity neighbour table,
   * the per-64-row-tile column sums / sums of squares the BatchNorm finalisation consumes."""
 import pytest
 import torch
@@ -44,10 +45,10 @@ def test_linear_rows_matches_matmul_and_tile_kernel(cuda_lib, cin, cout, m):
     assert (got - want).abs().max() <= 2e-6 * max(1.0, want.abs().max().item()) * max(1, cin) ** 0.5
     if ops.ceil4(cout) != cout:
         assert bool((out[:, cout:] == -7.0).all())             # padding columns are the caller's
-    # identity neighbour table -> spconv_kernel (gather-GEMM tile): same accumulation order, bit-identical rows
+    # identity neighbour table -> spconv_kernel (fp32 FFMA gather-GEMM tile)
     nbr = torch.arange(m, dtype=torch.int32, device="cuda").view(m, 1).contiguous()
     ref, ref_part = run_linear(L, xc, cin, Wc, cout, bc, m, nbr=nbr)
-    assert torch.equal(out[:, :cout], ref[:, :cout])
+    assert (out[:, :cout] - ref[:, :cout]).abs().max().item() <= 2e-6 * max(1.0, want.abs().max().item()) * max(1, cin) ** 0.5
     # per-tile column statistics: exact up to the summation order inside a 64-row tile
     tiles = out[:, :cout].cpu().double().split(64)
     s = torch.stack([t.sum(0) for t in tiles])

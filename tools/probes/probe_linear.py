@@ -1,4 +1,5 @@
-"""Dense per-row linears of the bench fragment (K == 1): linear_rows_kernel vs the gather-GEMM tile kernel (identity table).
+"""Dense per-row linears of the bench fragment (K == 1): the shipped kernel (EPRECON_LINEAR: 2 = linear_mma_kernel, default; 1 =
+linear_rows_kernel) vs the gather-GEMM tile kernel (identity table).
 
     python tools/probes/probe_linear.py > gpurun_out/r02_probe_linear_rows.json
 """
@@ -55,6 +56,6 @@ for m, cin, cout in SHAPES:
     for tag, flush in (("warm", False), ("flushed", True)):      # warm: operands L2-resident, as right after their producer
         new = timed(lambda: run(0), flush)
         old = timed(lambda: run(nbr.data_ptr()), flush)
-        rec.update({f"rows_us_{tag}": round(new, 1), f"tile_us_{tag}": round(old, 1), f"rows_GBs_{tag}": round(b / new / 1e3)})
+        rec.update({f"linear_us_{tag}": round(new, 1), f"tile_us_{tag}": round(old, 1), f"linear_GBs_{tag}": round(b / new / 1e3)})
     rows.append(rec)
 print(json.dumps({"linear": rows}, indent=1))
