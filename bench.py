@@ -350,6 +350,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     K = args.steps
     S = max(1, int(os.environ.get("EPRECON_STREAMS", str(DEFAULT_STREAMS))))   # fragments in flight per GPU
+    # host wait policy in stream drains: blocking once ranks x (streams + 1) threads outnumber the cores (spinning waiters
+    # starve the threads that have launches to issue); EPRECON_SYNC=auto|spin|yield|blocking overrides
+    from eprecon_b200.streams import set_sync_mode
+    sync_mode = os.environ.get("EPRECON_SYNC") or ("blocking" if world * (S + 1) > (os.cpu_count() or 1) else "auto")
+    set_sync_mode(sync_mode, dev)
     wl_name = args.workload
     wl = WORKLOADS[wl_name]
     stream_len = wl["stream_len"]
@@ -490,7 +495,9 @@ def run_ours(args):
     # ---- timed region: EXACTLY K steps of S fragments each, device-timed, max over ranks
     for s_ in range(S):
         counters[s_] = 0 if stream_len == 1 else stream_len * ((counters[s_] + stream_len - 1) // stream_len)   # streams start a fresh scene
+    cpu0 = time.process_time()
     ms = run_steps(K, body)
+    host_cpu_ms = (time.process_time() - cpu0) * 1e3 / (S * K)   # this rank's CPU time (all threads) per fragment; spin-waits count
     value = world * S * K / (ms / 1e3)
 
     # ---- e2e: host (pinned) inputs -> H2D -> forward -> D2H of the sparse TSDF, every fragment, on its own stream
@@ -659,7 +666,8 @@ def run_ours(args):
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["text"], "fragments_per_step": S * world,
-                       "streams_per_gpu": S, "step": f"{S} independent fragments in flight per GPU (one CUDA stream + host thread each, "
+                       "streams_per_gpu": S, "host_sync": sync_mode, "host_cpu_ms_per_fragment": round(host_cpu_ms, 2),
+                       "host_cpus": os.cpu_count(), "step": f"{S} independent fragments in flight per GPU (one CUDA stream + host thread each, "
                                                      "shared weights); value = fragments completed / device time",
                        "sizes": fs.nets[0].last_sizes, "thresholds": cfg.THRESHOLDS, "caps": cfg.TRAIN_NUM_SAMPLE,
                        "operands": "sparse-conv operands are fp16 pairs h + l*2^-11 (22 significant bits, as 3xTF32), fp32 accumulation" if ops.SPCONV_IMPL == "hl" else ops.SPCONV_IMPL,

@@ -40,7 +40,7 @@ def parse_header(path=HEADER_PATH):
 _lib = None
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); anything not listed launches one kernel
-KERNELS_PER_CALL = {"ep_version": 0, "ep_backproject_workspace_bytes": 0, "ep_compact_workspace_bytes": 0,
+KERNELS_PER_CALL = {"ep_version": 0, "ep_set_sync_mode": 0, "ep_backproject_workspace_bytes": 0, "ep_compact_workspace_bytes": 0,
                     "ep_sort_segments_workspace_bytes": 0, "ep_spconv_num_row_tiles": 0, "ep_spconv_tc_workspace_bytes": 0, "ep_spconv_hl_workspace_bytes": 0, "ep_hl_slabs": 0, "ep_hl_set_timeline": 0, "ep_spconv_hl_launches": 0, "ep_hl_debug_code": 0, "ep_bn2d_workspace_bytes": 0, "ep_bn2d_train": 2, "ep_backproject_count": 3, "ep_backproject_fused": 3, "ep_backproject_fused_workspace_bytes": 0,
                     "ep_compact_flags": 3, "ep_sort_segments": 14, "ep_hash_build": 2,
                     # native executor calls report their own launch count (executor.py adds it)

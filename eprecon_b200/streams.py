@@ -66,10 +66,23 @@ class _Future:
         return self._val
 
 
+SYNC_MODES = {"auto": 0, "spin": 1, "yield": 2, "blocking": 4}
+
+
+def set_sync_mode(mode, device=None):
+    """How host threads wait for the GPU in stream drains on `device` (ep_set_sync_mode): 'auto' (driver default: spin),
+    'spin', 'yield' or 'blocking'.  Use 'blocking' when streams x processes exceed the cores of the box."""
+    from . import _lib
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        _lib.check(_lib.lib().ep_set_sync_mode(SYNC_MODES[mode]), "ep_set_sync_mode")
+
+
 class FragmentStreams:
-    def __init__(self, net, n_streams, device=None):
+    def __init__(self, net, n_streams, device=None, sync_mode=None):
         assert n_streams >= 1
         self.device = device if device is not None else next(net.parameters()).device
+        if sync_mode is not None:
+            set_sync_mode(sync_mode, self.device)
         self.nets = [net] + [replicate(net) for _ in range(n_streams - 1)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
         self._queues = [queue.SimpleQueue() for _ in range(n_streams)]

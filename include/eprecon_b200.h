@@ -30,6 +30,8 @@ typedef struct CUstream_st* cudaStream_t;
 #define EP_ERR_UNSUPPORTED (-4)
 
 int ep_version(void);
+/* host wait policy of stream synchronisation on the current device: 0 default, 1 spin, 2 yield, 4 blocking (csrc/capi.cu) */
+int ep_set_sync_mode(int mode);
 
 /* ---- multi-view back-projection ---------------------------------------------------------------------------
  * replaces models/occupancy_initialization.py:189-261 (Back_Project.forward), :79-128 (init-stage projection +
