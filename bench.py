@@ -41,7 +41,7 @@ PORT_NOTE = ("; the arm is oracle/restate.py, a CPU restatement of the reference
              "under tests/golden/ -- the reference modules themselves need torchsparse / spconv (not installable offline) and "
              "/root/reference does not exist on the GPU box")
 METRIC = "fragments/sec (9x640x480, 3-level 96^3)"
-DEFAULT_STREAMS = 8   # fragments in flight per GPU (EPRECON_STREAMS overrides); 1/4/8 streams measured 44/70/81 fragments/s
+DEFAULT_STREAMS = 8   # fragments per step per GPU, and the streams in flight when the box has the cores (EPRECON_STREAMS / EPRECON_FRAGMENTS_PER_STEP override)
 WORKLOAD = "configs[1]: single 9-view 640x480 fragment, 3-level 24/48/96^3 @4cm, GRU fusion (fresh scene), TSDF+occ heads"
 # --workload variants make BASELINE configs[2] / configs[4] driver-runnable (the default stays configs[1], the one `metric` is quoted on)
 WORKLOADS = {
@@ -349,11 +349,23 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     K = args.steps
-    S = max(1, int(os.environ.get("EPRECON_STREAMS", str(DEFAULT_STREAMS))))   # fragments in flight per GPU
-    # host wait policy in stream drains: blocking once ranks x (streams + 1) threads outnumber the cores (spinning waiters
-    # starve the threads that have launches to issue); EPRECON_SYNC=auto|spin|yield|blocking overrides
+    # A step is F fragments per GPU whatever N is (weak scaling: fixed per-GPU work); S of them are in flight at a time (one
+    # host thread + CUDA stream each).  S is host tuning: 8 while every rank has >= 8 cores to itself, fewer on a crowded box
+    # (8 ranks on 32 CPUs: 736 fragments/s with 8 streams per rank, 803 with 4 -- profiles/r02_bench_n8_v14_*.json).
+    cpus = os.cpu_count() or 1
+    auto_s = DEFAULT_STREAMS
+    while auto_s > 2 and auto_s > cpus // max(world, 1):
+        auto_s //= 2
+    S = max(1, int(os.environ.get("EPRECON_STREAMS", str(auto_s))))   # fragments in flight per GPU
+    F = max(1, int(os.environ.get("EPRECON_FRAGMENTS_PER_STEP", str(DEFAULT_STREAMS))))
+    F = S * ((max(F, S) + S - 1) // S)                                 # whole rounds of the S streams
+    lanes_of = [list(range(w * (F // S), (w + 1) * (F // S))) for w in range(S)]   # lane = one fragment slot of a step (one scene stream)
+    worker_of = {lane: w for w, ls in enumerate(lanes_of) for lane in ls}
+    # host wait policy in stream drains: yield once ranks x (streams + 1) threads outnumber the cores (spinning waiters starve
+    # the threads that have launches to issue: N=8 on 32 CPUs 606 fragments/s spinning, 636 blocking, 736 yielding,
+    # profiles/r02_bench_n8_v13_*.json); EPRECON_SYNC=auto|spin|yield|blocking overrides
     from eprecon_b200.streams import set_sync_mode
-    sync_mode = os.environ.get("EPRECON_SYNC") or ("blocking" if world * (S + 1) > (os.cpu_count() or 1) else "auto")
+    sync_mode = os.environ.get("EPRECON_SYNC") or ("yield" if world * (S + 1) > (os.cpu_count() or 1) else "auto")
     set_sync_mode(sync_mode, dev)
     wl_name = args.workload
     wl = WORKLOADS[wl_name]
@@ -367,7 +379,7 @@ def run_ours(args):
     net.with_panoptic = bool(wl["panoptic"])
     fs = FragmentStreams(net, S, dev)   # S replicas over the same weights, one host thread + CUDA stream each
     # configs[2] wires the scene-level fusion behind NeuConNet exactly as models/neuralrecon.py:58-72 does
-    scene_fusers = [GRUFusion(cfg, direct_substitute=True, trianing=False) for _ in range(S)] if wl["panoptic"] else None
+    scene_fusers = [GRUFusion(cfg, direct_substitute=True, trianing=False) for _ in range(F)] if wl["panoptic"] else None
 
     # distinct input fragments: 1 (every rank / stream: its own copy of the same-shape fragment, weak scaling) or the 16 of a scene stream
     hosts = []
@@ -387,7 +399,7 @@ def run_ours(args):
         resident = [h.to_device(dev) for h in hosts]
     torch.cuda.synchronize()
     rel = ((inputs0["vol_origin_partial"][0] - inputs0["vol_origin"][0]) / cfg.VOXEL_SIZE).long()
-    counters = [0] * S
+    counters = [0] * F
 
     def fragment(net_r, dev_in, tag, slot=0, frag=0, cycle=0):
         ins = dict(dev_in["inputs"])
@@ -407,10 +419,10 @@ def run_ours(args):
         c = counters[slot]
         counters[slot] += 1
         f = c % stream_len
-        src = resident[f] if stream_len > 1 else resident[(k * S + slot) % n_copies]
+        src = resident[f] if stream_len > 1 else resident[(k * F + slot) % n_copies]
         return fragment(net_r, src, tag, slot, f, c // stream_len)
 
-    box_lo = [[int(rel[0]) + (rank * S + s) * 24, int(rel[1]), int(rel[2])] for s in range(S)]   # scenes side by side along x
+    box_lo = [[int(rel[0]) + (rank * F + s) * 24, int(rel[1]), int(rel[2])] for s in range(F)]   # scenes side by side along x
     box_hi = [[lo[0] + cfg.N_VOX[0], lo[1] + cfg.N_VOX[1], lo[2] + cfg.N_VOX[2]] for lo in box_lo]
     shifts = [torch.tensor(lo, dtype=torch.int32, device=dev) for lo in box_lo]
     skip_exchange = bool(os.environ.get("EPRECON_BENCH_NO_EXCHANGE"))   # diagnostic: split exchange cost from host contention
@@ -441,28 +453,29 @@ def run_ours(args):
         barrier()
         e0.record()
 
-        def job(slot):
+        def job(worker):
             def run(net_r, stream):
                 stream.wait_event(e0)
                 for k in range(n_steps):
-                    uid[0] += 1
-                    out = step_body(net_r, slot, k, f"s{slot}_{uid[0]}")
-                    if world > 1:
-                        ev = torch.cuda.Event()
-                        ev.record(stream)
-                        done.put((k, slot, out, ev))
+                    for slot in lanes_of[worker]:
+                        uid[0] += 1
+                        out = step_body(net_r, slot, k, f"s{slot}_{uid[0]}")
+                        if world > 1:
+                            ev = torch.cuda.Event()
+                            ev.record(stream)
+                            done.put((k, slot, out, ev))
                 stream.synchronize()
             return run
-        futs = [fs.submit(s, job(s)) for s in range(S)]
+        futs = [fs.submit(w, job(w)) for w in range(S)]
         if world > 1:
             pending = {}
             main = torch.cuda.current_stream()
             for k in range(n_steps):
-                while len(pending.get(k, {})) < S:
+                while len(pending.get(k, {})) < F:
                     kk, slot, out, ev = done.get()
                     pending.setdefault(kk, {})[slot] = (out, ev)
                 outs = []
-                for s in range(S):
+                for s in range(F):
                     out, ev = pending[k][s]
                     main.wait_event(ev)
                     for t in (out["coords"], out["tsdf"]):
@@ -486,19 +499,19 @@ def run_ours(args):
     if rank == 0:
         sampler.start()   # started before the warm-up so that its process start-up stays out of the timed region
     # warm-up: first each replica alone (graph capture, lazily built constant tables), then W concurrent steps
-    fs.warm(lambda net_r, stream: fragment(net_r, resident[0], f"warm{id(net_r)}", fs.nets.index(net_r), 0, -1))
+    fs.warm(lambda net_r, stream: fragment(net_r, resident[0], f"warm{id(net_r)}", lanes_of[fs.nets.index(net_r)][0], 0, -1))
     W = max(args.warmup, 3)
     run_steps(W, body)
     if rank == 0:
         sampler.rows.clear()   # keep only samples taken under load (timed region + e2e loop)
 
-    # ---- timed region: EXACTLY K steps of S fragments each, device-timed, max over ranks
-    for s_ in range(S):
+    # ---- timed region: EXACTLY K steps of F fragments each, device-timed, max over ranks
+    for s_ in range(F):
         counters[s_] = 0 if stream_len == 1 else stream_len * ((counters[s_] + stream_len - 1) // stream_len)   # streams start a fresh scene
     cpu0 = time.process_time()
     ms = run_steps(K, body)
-    host_cpu_ms = (time.process_time() - cpu0) * 1e3 / (S * K)   # this rank's CPU time (all threads) per fragment; spin-waits count
-    value = world * S * K / (ms / 1e3)
+    host_cpu_ms = (time.process_time() - cpu0) * 1e3 / (F * K)   # this rank's CPU time (all threads) per fragment; spin-waits count
+    value = world * F * K / (ms / 1e3)
 
     # ---- e2e: host (pinned) inputs -> H2D -> forward -> D2H of the sparse TSDF, every fragment, on its own stream
     stage1 = [DeviceStage(hosts[0], dev) for _ in range(S)]   # all fragments of a workload have the same packed layout
@@ -511,24 +524,24 @@ def run_ours(args):
         c = counters[slot]
         counters[slot] += 1
         f = c % stream_len
-        st = stage1[slot]
+        st = stage1[worker_of[slot]]
         st.host = hosts[f]             # the step's own fragment: one pinned->device copy per dtype (fp32 features/matrices, bool GT occupancy)
         dev_in = st.load()
         o = fragment(net_r, dev_in, tag, slot, f, c // stream_len)
         n = o["coords"].shape[0]
-        coords_h[slot][:n].copy_(o["coords"], non_blocking=True)
-        tsdf_h[slot][:n].copy_(o["tsdf"], non_blocking=True)
+        coords_h[worker_of[slot]][:n].copy_(o["coords"], non_blocking=True)
+        tsdf_h[worker_of[slot]][:n].copy_(o["tsdf"], non_blocking=True)
         d2h[0] = n * (4 * 8 + 4)
         torch.cuda.current_stream().synchronize()   # the caller holds the result on the host before the next fragment
         return o
 
-    for s_ in range(S):
+    for s_ in range(F):
         counters[s_] = stream_len * ((counters[s_] + stream_len - 1) // stream_len)
     run_steps(1, e2e_fragment)
-    for s_ in range(S):
+    for s_ in range(F):
         counters[s_] = stream_len * ((counters[s_] + stream_len - 1) // stream_len)
     ms_e2e = run_steps(K, e2e_fragment)
-    e2e_value = world * S * K / (ms_e2e / 1e3)
+    e2e_value = world * F * K / (ms_e2e / 1e3)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- single-stream pass on the main thread: latency of one fragment, per-launch CUDA-event durations of the two
@@ -665,19 +678,19 @@ def run_ours(args):
             "metric": wl["metric"], "value": value, "unit": "fragments/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["text"], "fragments_per_step": S * world,
+            "config": {"workload": wl["text"], "fragments_per_step": F * world, "fragments_per_step_per_gpu": F,
                        "streams_per_gpu": S, "host_sync": sync_mode, "host_cpu_ms_per_fragment": round(host_cpu_ms, 2),
-                       "host_cpus": os.cpu_count(), "step": f"{S} independent fragments in flight per GPU (one CUDA stream + host thread each, "
+                       "host_cpus": os.cpu_count(), "step": f"{F} independent fragments per GPU, {S} in flight at a time (one CUDA stream + host thread each, "
                                                      "shared weights); value = fragments completed / device time",
                        "sizes": fs.nets[0].last_sizes, "thresholds": cfg.THRESHOLDS, "caps": cfg.TRAIN_NUM_SAMPLE,
                        "operands": "sparse-conv operands are fp16 pairs h + l*2^-11 (22 significant bits, as 3xTF32), fp32 accumulation" if ops.SPCONV_IMPL == "hl" else ops.SPCONV_IMPL,
                        "l2": f"inputs rotated over {n_copies} HBM-resident fragments ({n_copies * feat_mb:.0f} MB of feature maps > 126 MB L2)",
-                       "multi_gpu": (f"{S} fragments per rank per step + NCCL send/recv of the step's sparse TSDF rows to the holder (rank 0) + one merge "
+                       "multi_gpu": (f"{F} fragments per rank per step + NCCL send/recv of the step's sparse TSDF rows to the holder (rank 0) + one merge "
                                      "kernel there" + (" [EXCHANGE DISABLED: diagnostic run]" if skip_exchange else "")) if world > 1 else "n/a"},
-            "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": h2d_bytes * S, "d2h_bytes_per_step": d2h[0] * S,
+            "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": h2d_bytes * F, "d2h_bytes_per_step": d2h[0] * F,
                     "ms_per_step": ms_e2e / K},
             "single_stream": single,
-            "gpu_launches": (launches_per_fragment or 0) * S * K, "gpu_launches_per_fragment": launches_per_fragment,
+            "gpu_launches": (launches_per_fragment or 0) * F * K, "gpu_launches_per_fragment": launches_per_fragment,
             "clocks": clocks, "roofline": roofline, "kernel_share": kernel_share, "cpu_baseline": cpu_baseline}))
     fs.close()
     if world > 1:

@@ -71,7 +71,8 @@ SYNC_MODES = {"auto": 0, "spin": 1, "yield": 2, "blocking": 4}
 
 def set_sync_mode(mode, device=None):
     """How host threads wait for the GPU in stream drains on `device` (ep_set_sync_mode): 'auto' (driver default: spin),
-    'spin', 'yield' or 'blocking'.  Use 'blocking' when streams x processes exceed the cores of the box."""
+    'spin', 'yield' or 'blocking'.  Use 'yield' when streams x processes exceed the cores of the box (measured best at
+    8 ranks x 8 streams on 32 CPUs; 'blocking' frees the cores completely but adds ~0.2 ms per drain)."""
     from . import _lib
     with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
         _lib.check(_lib.lib().ep_set_sync_mode(SYNC_MODES[mode]), "ep_set_sync_mode")
