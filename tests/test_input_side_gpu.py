@@ -42,7 +42,8 @@ def test_batched_backbones_feed_neucon(cuda_lib):
     inputs, fa0, fb0 = synth.make_fragment(seed=1, image_hw=(240, 320), n_vox=(64, 64, 64))
     g = torch.Generator().manual_seed(3)
     imgs = (torch.rand(1, 9, 3, 240, 320, generator=g) * 255.0).cuda()
-    with torch.no_grad():
+    # fp32 convolutions on both sides (cuDNN would otherwise pick TF32 kernels, and different ones for 1 and 9 images)
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         fa, fb = fx(imgs)
         x = fx.normalizer(imgs)
         for v in (0, 4, 8):
@@ -50,7 +51,7 @@ def test_batched_backbones_feed_neucon(cuda_lib):
             for lvl in range(3):
                 assert fa[v][lvl].shape == fa0[v][lvl].shape                      # the pyramid layout synth.make_fragment mimics
                 scale = want[lvl].abs().max()
-                assert ((fa[v][lvl] - want[lvl]).abs().max() / scale).item() < 1e-4
+                assert ((fa[v][lvl] - want[lvl]).abs().max() / scale).item() < 2e-4
     cfg = synth.make_cfg(n_vox=(64, 64, 64))
     cfg.THRESHOLDS = [-100.0, -100.0, -100.0]          # random-init backbone features: keep every voxel so all levels run
     net = NeuConNet(cfg)
