@@ -643,7 +643,7 @@ def run_ours(args):
                  "tf32": "spconv_tc_kernel<1> (gather -> tcgen05.mma kind::tf32)",
                  "ffma": "spconv_kernel (gather-GEMM, fp32 FFMA)"}[impl_name]
         ach = flops / (sp_ms * 1e-3) / 1e12 if sp_ms else 0.0
-        roofline = {"kernel": kname + "; K=1 linears run on spconv_kernel (fp32 FFMA)", "bound": "tensor", "achieved": ach,
+        roofline = {"kernel": kname + "; K=1 linears run on linear_mma_kernel (mma.sync 3xTF32 rows; 192-wide weights on the fp32 FFMA tile kernel)", "bound": "tensor", "achieved": ach,
                     "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak, "traffic": traffic, "traffic_note": traffic_note,
                     "measured": where,
                     "peak_source": src + ", bf16 dense sustained; achieved counts the algorithmic 2*Cin*Cout*pairs flops once (the "
