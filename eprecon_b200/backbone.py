@@ -22,13 +22,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-def _round_to_multiple_of(val, divisor, round_up_bias=0.9):
-    new_val = max(divisor, int(val + divisor / 2) // divisor * divisor)
-    return new_val if new_val >= round_up_bias * val else new_val + divisor
-
-
 def _get_depths(alpha):
-    return [_round_to_multiple_of(d * alpha, 8) for d in (32, 16, 24, 40, 80, 96, 192, 320)]
+    """Channel widths of the MNASNet stages (torchvision's own rounding rule; the reference restates it, backbone.py:6-19)."""
+    from torchvision.models.mnasnet import _get_depths as tv_depths
+    return tv_depths(alpha)
 
 
 class ViewBatchNorm2d(nn.BatchNorm2d):
