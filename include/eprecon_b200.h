@@ -126,10 +126,11 @@ size_t ep_spconv_tc_workspace_bytes(int64_t m_out, int npad, int K);
 int ep_spconv_tc_fwd(const float* in, int ld_in, int cin, const int32_t* nbr, int K, const float* w_hi,
                      const float* w_lo, int npad, int cout, const float* bias, float* out, int ld_out, int64_t m_out,
                      float* bn_partial, int prec, void* workspace, size_t workspace_bytes, cudaStream_t stream);
-/* TMA-gather variant (csrc/spconv_hl.cu): operands are PRE-SPLIT half pairs -- x = h + l * 2^-11, h = fp16(x), 22 significant
- * bits like 3xTF32 at half the bytes -- stored in 32-channel slabs of 128 bytes [32 h | 32 l], the SWIZZLE_128B row of a K-major
- * tcgen05 operand; rows are fetched by cp.async.bulk.tensor tile::gather4 straight from the neighbour table (no LDG/STS on
- * the operand path), tcgen05.mma kind::f16 with fp32 accumulators in TMEM.  in_hl [m_in][nslab][64] halfs, nslab = ceil(cin / 32);
+/* Shipped tensor-core variant (csrc/spconv_hl.cu): operands are PRE-SPLIT half pairs -- x = h + l * 2^-11, h = fp16(x), 22
+ * significant bits like 3xTF32 at half the bytes -- stored in 32-channel slabs of 128 bytes [32 h | 32 l], the SWIZZLE_128B row
+ * of a K-major tcgen05 operand; rows are gathered through the neighbour table by 16-byte cp.async straight into that layout
+ * (default; EPRECON_HL_PRODUCER=tma selects the measured-slower cp.async.bulk.tensor tile::gather4 producer), weight slabs by
+ * TMA, tcgen05.mma kind::f16 with fp32 accumulators in TMEM.  in_hl [m_in][nslab][64] halfs, nslab = ceil(cin / 32);
  * w_hl [K][nslab][npad][64] halfs; npad = cout rounded up to 16 (to 128 when larger). */
 int ep_hl_slabs(int c);
 int ep_hl_split_rows(const float* src, int ld_src, int c, int64_t m, uint16_t* dst, int32_t* overflow, cudaStream_t stream);
@@ -214,6 +215,12 @@ size_t ep_masked_attention_workspace_bytes(int64_t n_keys, int n_heads);
 int ep_masked_attention(const float* q, const float* k, const float* v, int ld_kv, const uint8_t* blocked, int64_t n_keys,
                         int n_queries, int n_heads, int head_dim, float scale, float* out, void* workspace,
                         size_t workspace_bytes, cudaStream_t stream);
+/* same, with a per-query flag (int32 [n_queries], optional): 0 = every key of that query is blocked, so the query ignores the
+ * mask -- the reference's "fully blocked query attends everywhere" rewrite (models/mask3dformer.py:392) without a pass over
+ * the flags */
+int ep_masked_attention_flagged(const float* q, const float* k, const float* v, int ld_kv, const uint8_t* blocked,
+                                const int32_t* row_unblocked, int64_t n_keys, int n_queries, int n_heads, int head_dim, float scale,
+                                float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- scene TSDF -> mesh: GPU marching cubes + nearest-voxel labels, replaces the CPU tail of the reference's
  * mesh export (utils.py:231-247 skimage.measure.marching_cubes + np.round / np.clip lookup; volumes from gru_fusion.py:217-257).
@@ -227,10 +234,6 @@ int ep_mc_vertices(const float* vol, int dx, int dy, int dz, float level, const 
                    cudaStream_t stream);
 int ep_mc_faces(const float* vol, int dx, int dy, int dz, float level, const int32_t* cell_index, const int32_t* tri_offset,
                 int64_t n_cells, const int32_t* edge_pos, int32_t* faces, cudaStream_t stream);
-
-int ep_masked_attention_flagged(const float* q, const float* k, const float* v, int ld_kv, const uint8_t* blocked,
-                                const int32_t* row_unblocked, int64_t n_keys, int n_queries, int n_heads, int head_dim, float scale,
-                                float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- panoptic decoder body as one native call (csrc/decoder.cu): MultiScaleMaskedTransformerDecoder.forward
  * (models/mask3dformer.py:337-445; layers :70-200; models/voxel_position_encoding.py:42-146) for the reference configuration
