@@ -193,6 +193,18 @@ def _cpu_threads():
     return max(1, min(os.cpu_count() or 1, 16))
 
 
+def _cpu_model():
+    """CPU model string of the host the CPU arm runs on (state it next to the core count)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def workload_cfg(name):
     """(cfg, fragment kwargs) of a --workload: shipped caps (config/test.yaml:29), thresholds calibrated per workload."""
     from eprecon_b200 import synth
@@ -260,7 +272,8 @@ def run_reference(args):
                       "config": {"workload": WORKLOADS[wl]["text"]},
                       "cpu_baseline": {"value": value, "unit": "fragments/s", "cores": cores, "kind": "port",
                                        "sample": SAMPLE_TEXT[lvl] + PORT_NOTE,
-                                       "fragment_fraction_per_step": SAMPLE_FRACTION[lvl], "host_cpus": os.cpu_count()},
+                                       "fragment_fraction_per_step": SAMPLE_FRACTION[lvl], "host_cpus": os.cpu_count(),
+                                       "cpu_model": _cpu_model()},
                       "e2e": {"value": value, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -670,7 +683,7 @@ def run_ours(args):
         lvl = pick_sample_level(probe, 1, 60.0)      # one step of ~20 s on 8-16 cores: the full fragment
         t = cpu_sample(1, 0, max_level=lvl, workload=wl_name)
         cpu_baseline = {"value": SAMPLE_FRACTION[lvl] / t, "unit": "fragments/s", "cores": _cpu_threads(), "host_cpus": os.cpu_count(),
-                        "kind": "port", "sample": SAMPLE_TEXT[lvl] + f"; {t:.1f} s of CPU work" + PORT_NOTE,
+                        "cpu_model": _cpu_model(), "kind": "port", "sample": SAMPLE_TEXT[lvl] + f"; {t:.1f} s of CPU work" + PORT_NOTE,
                         "fragment_fraction_per_step": SAMPLE_FRACTION[lvl]}
 
     if rank == 0:
